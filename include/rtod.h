@@ -1,0 +1,150 @@
+/*
+ * rtod.h -- C ABI of librtod.so, the B200-native (sm_100a) YOLOv3 detection hot path.
+ *
+ * The reference (uguryagmur/RealTimeObjectDetection) has no FFI: its boundary is the Python
+ * surface of src/darknet.py and src/util.py.  Each entry point below names the reference
+ * interface it replaces; the Python mirror of that interface
+ * (realtimeobjectdetection_b200/{darknet,util}.py) binds these symbols with ctypes and keeps
+ * the reference's names, argument order and return conventions.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer owned by the
+ *     caller unless the name says _host; the library allocates no device memory;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is
+ *     enqueued asynchronously on it, no hidden synchronisation, CUDA-graph capturable;
+ *   - return value 0 = RTOD_OK, negative = error; rtod_last_error() returns a thread-local
+ *     human-readable message for the last failing call on this thread;
+ *   - never throws, exits or prints.
+ */
+#ifndef RTOD_H_
+#define RTOD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTOD_ABI_VERSION 1
+
+enum {
+    RTOD_OK = 0,
+    RTOD_ERR_BAD_ARG = -1,      /* null pointer, negative size, inconsistent shapes          */
+    RTOD_ERR_UNSUPPORTED = -2,  /* a shape/option the kernels do not implement               */
+    RTOD_ERR_CAPACITY = -3,     /* caller-provided buffer/workspace too small                */
+    RTOD_ERR_CUDA = -4,         /* a CUDA runtime/driver call failed (see rtod_last_error)   */
+    RTOD_ERR_STATE = -5,        /* call order violated (e.g. forward before bind/weights)    */
+    RTOD_ERR_DEVICE = -6        /* kernel-side failure flag (pipeline time-out, bad tile)    */
+};
+
+/* Block types of a Darknet cfg (src/darknet.py:460-526). */
+enum {
+    RTOD_LAYER_CONV = 0,
+    RTOD_LAYER_SHORTCUT = 1,
+    RTOD_LAYER_ROUTE = 2,
+    RTOD_LAYER_UPSAMPLE = 3,
+    RTOD_LAYER_MAXPOOL = 4,
+    RTOD_LAYER_YOLO = 5
+};
+
+#define RTOD_MAX_ANCHORS 8
+
+/* One parsed cfg block, already resolved the way Darknet.create_modules does
+ * (src/darknet.py:449-603): `pad` is the effective padding ((size-1)/2 iff cfg pad != 0),
+ * route/shortcut sources are ABSOLUTE layer indices (-1 = unused). */
+typedef struct RtodLayerDesc {
+    int32_t type;             /* RTOD_LAYER_*                                              */
+    int32_t filters;          /* conv: output channels                                     */
+    int32_t size;             /* conv / maxpool: kernel size                               */
+    int32_t stride;           /* conv / maxpool: stride                                    */
+    int32_t pad;              /* conv: effective zero padding                              */
+    int32_t batch_normalize;  /* conv: 1 = BatchNorm2d follows (folded, eval semantics)    */
+    int32_t leaky;            /* conv: 1 = LeakyReLU(0.1) follows, 0 = linear              */
+    int32_t src0;             /* shortcut: i-1; route: first source                        */
+    int32_t src1;             /* shortcut: i+from; route: second source or -1              */
+    int32_t num_anchors;      /* yolo: anchors selected by mask                            */
+    int32_t classes;          /* yolo: number of classes                                   */
+    float anchors[2 * RTOD_MAX_ANCHORS]; /* yolo: (w,h) pixel pairs in mask order          */
+} RtodLayerDesc;
+
+typedef struct RtodPlan RtodPlan;
+
+/* plan flags */
+#define RTOD_PLAN_KEEP_ALL 1u     /* no buffer reuse: every layer output stays readable    */
+#define RTOD_PLAN_CONV_SIMT 2u    /* validation only: CUDA-core convs instead of tcgen05   */
+
+int rtod_abi_version(void);
+const char* rtod_last_error(void);
+
+/* ---- Darknet.__init__ / create_modules (src/darknet.py:176-189, 449-603) --------------
+ * Builds the execution plan (shape inference, NHWC buffer liveness plan, concat aliasing,
+ * per-layer kernel selection) for a fixed input shape [batch, in_c, in_h, in_w];
+ * inp_dim is int(net_info["height"]) used by the decode (src/darknet.py:258). */
+int rtod_plan_create(const RtodLayerDesc* layers, int n_layers, int batch, int in_c, int in_h,
+                     int in_w, int inp_dim, unsigned flags, RtodPlan** out_plan);
+void rtod_plan_destroy(RtodPlan* plan);
+size_t rtod_plan_workspace_bytes(const RtodPlan* plan);   /* activations + head logits     */
+size_t rtod_plan_weight_bytes(const RtodPlan* plan);      /* packed bf16 weights + biases  */
+int rtod_plan_num_rows(const RtodPlan* plan);             /* N of the [B, N, 5+C] output   */
+int rtod_plan_num_attrs(const RtodPlan* plan);            /* 5+C (0 if no yolo layer)      */
+int rtod_plan_layer_shape(const RtodPlan* plan, int layer, int* c, int* h, int* w);
+int rtod_plan_launch_count(const RtodPlan* plan);         /* kernels per forward           */
+double rtod_plan_conv_flops(const RtodPlan* plan);        /* 2*M*N*K summed over convs     */
+
+/* Binds caller-owned device arenas (256-byte aligned) and encodes the TMA descriptors. */
+int rtod_plan_bind(RtodPlan* plan, void* workspace, size_t workspace_bytes, void* weight_arena,
+                   size_t weight_bytes);
+
+/* ---- Darknet.load_weights / load_state_dict (src/darknet.py:316-410) -------------------
+ * Folds BatchNorm (eval: w' = w*g/sqrt(var+eps), b' = beta - mean*g/sqrt(var+eps)) and
+ * re-lays the fp32 [Cout,Cin,k,k] weight out as K-major bf16 [Cout_pad][k*k*Cin] on device.
+ * bias may be null (BN convs); the four BN pointers are null for convs without BN. */
+int rtod_plan_set_conv_weights(RtodPlan* plan, int layer, const float* weight, const float* bias,
+                               const float* bn_gamma, const float* bn_beta, const float* bn_mean,
+                               const float* bn_var, float bn_eps, void* stream);
+
+/* ---- Darknet.forward (src/darknet.py:199-253) ------------------------------------------
+ * x: [batch, in_c, in_h, in_w] fp32 NCHW; pred: [batch, N, 5+C] fp32.  train != 0 selects the
+ * TRAIN=True decode (sigmoids only, src/util.py:211).  pred may be null when the cfg has no
+ * yolo layer. */
+int rtod_plan_forward(RtodPlan* plan, const float* x_nchw, float* pred, int train, void* stream);
+
+/* Debug/validation: copy one layer's output to fp32 NCHW [batch, c, h, w].  Meaningful after a
+ * forward of a plan created with RTOD_PLAN_KEEP_ALL (or for the last layer). */
+int rtod_plan_read_layer(RtodPlan* plan, int layer, float* out_nchw, void* stream);
+/* Polls the device-side failure flag of the last forward (synchronises the stream). */
+int rtod_plan_check(RtodPlan* plan, void* stream);
+
+/* ---- util.predict_transform (src/util.py:175-239) -------------------------------------
+ * head: [B, A*(5+C), G, G] fp32 NCHW -> out: [B, G*G*A, 5+C] fp32; anchors_host: A (w,h) pixel
+ * pairs in HOST memory; stride = inp_dim / G. */
+int rtod_yolo_decode(const float* head_nchw, int B, int G, int A, int C, int inp_dim,
+                     const float* anchors_host, int train, float* out, void* stream);
+
+/* ---- util.write_results (+confidence_mask, bbox_iou inside it; src/util.py:242-346) -----
+ * pred: [B, N, 5+C] fp32 (not modified).  out_rows: [cap, 8] fp32 rows
+ * [img, x1, y1, x2, y2, obj, cls_conf, cls] ordered image, class ascending, objectness
+ * descending (ties: lower row index first).  *out_count (device int) receives the number of
+ * detections D; rows beyond cap are dropped (D may exceed cap: compare after the copy back).
+ * Limits: C <= 4096, N <= 2^20. */
+size_t rtod_write_results_workspace_bytes(int B, int N, int C);
+int rtod_write_results(const float* pred, int B, int N, int C, float confidence, float nms_conf,
+                       float* out_rows, int cap, int* out_count, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ---- util.confidence_mask (src/util.py:106-117) -- out = pred * (pred[...,4] > conf) */
+int rtod_confidence_mask(const float* pred, long long rows, int attrs, float confidence, float* out,
+                         void* stream);
+
+/* ---- util.bbox_iou (src/util.py:120-153) --------------------------------------------------
+ * box1: n1 boxes, box2: n2 boxes, rows of `stride` floats whose first four are x1,y1,x2,y2;
+ * n1 == n2, or one of them == 1 (broadcast).  out: max(n1,n2) fp32 IoUs (+1 pixel convention,
+ * every operation individually rounded like the reference's tensor ops). */
+int rtod_bbox_iou(const float* box1, int n1, int stride1, const float* box2, int n2, int stride2,
+                  float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTOD_H_ */

@@ -102,6 +102,7 @@ class DarknetPort:
         outputs = {}
         heads = []
         self.anchors = None
+        self.layer_outputs = outputs            # kept for layer-wise parity checks
         for i, blk in enumerate(self.blocks[1:]):
             kind = blk["type"]
             if kind == "convolutional":

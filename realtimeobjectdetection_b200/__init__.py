@@ -1,0 +1,17 @@
+"""B200-native (sm_100a) YOLOv3 detection hot path with the reference's Python API.
+
+    from realtimeobjectdetection_b200 import Darknet, write_results
+    model = Darknet(cfg_path, CUDA=True); model.load_weights(path)
+    pred = model(x)                                   # [B, N, 5+C]  (src/darknet.py:199-253)
+    det = write_results(pred, 80, 0.5, 0.4)           # [D, 8] or 0  (src/util.py:242-346)
+
+Everything numerical runs in ``librtod.so`` (hand-written CUDA, C ABI in include/rtod.h); this
+package is the host-side mirror of the reference interface.  Importing it does not need a GPU;
+calling it does, and there is no CPU fallback.
+"""
+from .cfg import builtin_cfg, parse_cfg  # noqa: F401
+from .darknet import Darknet, DetectionLayer, EmptyLayer, MaxPoolStride1  # noqa: F401
+from .util import bbox_iou, confidence_mask, predict_transform, write_results  # noqa: F401
+
+__all__ = ["Darknet", "DetectionLayer", "EmptyLayer", "MaxPoolStride1", "bbox_iou",
+           "confidence_mask", "predict_transform", "write_results", "builtin_cfg", "parse_cfg"]

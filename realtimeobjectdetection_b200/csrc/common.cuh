@@ -1,0 +1,77 @@
+// common.cuh -- shared host/device helpers for librtod (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/rtod.h"
+
+namespace rtod {
+
+// ---------------------------------------------------------------------------------------
+// error reporting: thread-local message, negative return codes (include/rtod.h)
+// ---------------------------------------------------------------------------------------
+char* last_error_buffer();          // api.cu
+constexpr int kErrBuf = 512;
+
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(last_error_buffer(), kErrBuf, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define RTOD_CUDA_OK(expr)                                                                    \
+    do {                                                                                      \
+        cudaError_t err__ = (expr);                                                           \
+        if (err__ != cudaSuccess)                                                             \
+            return ::rtod::fail(RTOD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                \
+                                cudaGetErrorString(err__), __FILE__, __LINE__);               \
+    } while (0)
+
+#define RTOD_LAUNCH_OK(what)                                                                  \
+    do {                                                                                      \
+        cudaError_t err__ = cudaGetLastError();                                               \
+        if (err__ != cudaSuccess)                                                             \
+            return ::rtod::fail(RTOD_ERR_CUDA, "launch of %s failed: %s (%s:%d)", what,       \
+                                cudaGetErrorString(err__), __FILE__, __LINE__);               \
+    } while (0)
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+constexpr int kNumSMs = 148;        // B200: 2 dies x 74 SMs
+
+// ---------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float leaky01(float v) { return v > 0.0f ? v : 0.1f * v; }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// logistic function with full-precision exp and IEEE division (reference: torch.sigmoid, fp32)
+__device__ __forceinline__ float sigmoid_f32(float v) {
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+}  // namespace rtod

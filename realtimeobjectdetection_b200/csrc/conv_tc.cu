@@ -1,0 +1,436 @@
+// conv_tc.cu -- convolution block of Darknet.forward (src/darknet.py:292-295, 467-501:
+// Conv2d [+ BatchNorm2d] [+ LeakyReLU(0.1)], and the shortcut add of :263-268) as ONE
+// sm_100a implicit-GEMM kernel:
+//
+//     D[M = B*Ho*Wo, N = Cout] = A[M, K = ks*ks*Cin] * W[N, K]^T        (bf16 x bf16 -> fp32)
+//
+//   * A (activations, NHWC bf16) is never materialised: a TMA im2col descriptor
+//     (cuTensorMapEncodeIm2col) gathers, for filter tap (ky,kx) and a 16/32/64-channel slice,
+//     the 128 consecutive output pixels of the tile straight into 128B/64B/32B-swizzled
+//     shared memory, zero-filling the padding halo and stepping by the conv stride.
+//     1x1 convolutions are a plain 2-D tiled descriptor over [M, Cin].
+//   * W (BN-folded, K-major bf16 [Cout_pad][K]) arrives through a 2-D tiled descriptor.
+//   * tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN<=256, K=16) accumulates in TMEM; one
+//     elected thread issues, tcgen05.commit releases shared-memory stages back to the TMA
+//     producer through mbarriers and finally publishes the accumulator to the epilogue.
+//   * four epilogue warps read TMEM with tcgen05.ld (32 lanes x 32 columns), add the folded
+//     bias, apply leaky 0.1, add the shortcut operand, and store NHWC bf16 (or the fp32 logits
+//     of a detection head) with 16-byte vector stores -- possibly into a channel slice of a
+//     route/concat buffer (src/darknet.py:285-288 becomes zero-copy).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue
+// (warp 2 also owns the TMEM allocation).  Every mbarrier wait is bounded: on a time-out the
+// kernel raises *err_flag and drains instead of hanging the GPU.
+#include "conv_tc.cuh"
+
+namespace rtod {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kBM = 128;
+constexpr unsigned long long kWaitTimeoutNs = 2000000000ull;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// bounded wait: false after a time-out or once another CTA has raised the failure flag
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 255u) == 0u) {
+            if (*(volatile int*)err_flag != 0) return false;
+            if (global_timer_ns() - t0 > kWaitTimeoutNs) {
+                atomicExch(err_flag, 2);
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                                   int c, int w, int h, int n, uint16_t off_w,
+                                                   uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, K-major operand whose rows are one swizzle span wide
+// (row_bytes = 32/64/128): start address, SBO = 8 rows, version 1, swizzle mode
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t row_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((8u * row_bytes) >> 4) << 32) |
+           (1ull << 46) | (layout << 61);
+}
+
+// =============================================================================================
+__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t row_bytes = (uint32_t)p.BK * 2u;
+    const uint32_t a_bytes = kBM * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* accum_bar = empty_bar + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int num_kb = p.ks * p.ks * p.cchunks;
+    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * p.BN;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.tmA);
+        prefetch_tmap(&p.tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int ow = 0, oh = 0, on = 0;
+            if (p.ks > 1) {                      // first output pixel of the tile -> input coords
+                ow = (m0 % p.Wo) * p.stride - p.pad;
+                oh = ((m0 / p.Wo) % p.Ho) * p.stride - p.pad;
+                on = m0 / (p.Wo * p.Ho);
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag)) break;
+                uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
+                mbar_expect_tx(&full_bar[stage], stage_bytes);
+                const int tap = kb / p.cchunks, c0 = (kb - tap * p.cchunks) * p.BK;
+                if (p.ks > 1)
+                    tma_load_im2col_4d(a_dst, &p.tmA, &full_bar[stage], c0, ow, oh, on,
+                                       (uint16_t)(tap % p.ks), (uint16_t)(tap / p.ks));
+                else
+                    tma_load_2d(a_dst, &p.tmA, &full_bar[stage], c0, m0);
+                tma_load_2d(a_dst + a_bytes, &p.tmB, &full_bar[stage], kb * p.BK, n0);
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                if (!mbar_wait(&full_bar[stage], phase, p.err_flag)) break;
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t b_addr = a_addr + a_bytes;
+                for (int k = 0; k < p.BK / 16; ++k)
+                    umma_bf16(tmem_base, smem_desc(a_addr + k * 32, row_bytes),
+                              smem_desc(b_addr + k * 32, row_bytes), p.idesc, (uint32_t)(kb | k));
+                umma_commit(&empty_bar[stage]);              // frees the stage when the MMAs retire
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            umma_commit(accum_bar);                          // accumulator complete
+        }
+    } else {
+        // ================= epilogue: TMEM -> registers -> global =================
+        const int quarter = warp & 3;                        // TMEM lanes [32*quarter, +32)
+        const bool ok = mbar_wait(accum_bar, 0u, p.err_flag);
+        tc_fence_after();
+        const long long m = (long long)m0 + quarter * 32 + lane;
+        const bool row_ok = ok && m < p.M;
+        for (int c = 0; c < p.BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
+            if (!row_ok) continue;
+            const int nc = n0 + c * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int n = nc + g * 8;
+                if (n >= p.store_limit) break;
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                float f[8];
+                f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
+                f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+                f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
+                f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+                f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
+                f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+                f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
+                f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+                if (p.leaky) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = leaky01(f[j]);
+                }
+                if (p.res) {
+                    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p.res + m * p.res_pitch + n));
+                    f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
+                    f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+                    f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
+                    f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+                }
+                if (p.out_fp32) {
+                    float* dst = reinterpret_cast<float*>(p.out) + m * p.out_pitch + n;
+                    *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                } else {
+                    uint4 o;
+                    o.x = pack_bf16x2(f[0], f[1]);
+                    o.y = pack_bf16x2(f[2], f[3]);
+                    o.z = pack_bf16x2(f[4], f[5]);
+                    o.w = pack_bf16x2(f[6], f[7]);
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.out_pitch + n) = o;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// ---- host: tensor-map encoding through the driver entry points (no libcuda link dependency) ---
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int driver_fn(const char* name, void** fn) {
+    cudaDriverEntryPointQueryResult q;
+    RTOD_CUDA_OK(cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !*fn)
+        return fail(RTOD_ERR_CUDA, "driver entry point %s unavailable", name);
+    return RTOD_OK;
+}
+
+CUtensorMapSwizzle swizzle_for(int bk) {
+    return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+int pick_bk(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : (cin % 16 == 0 ? 16 : 0)); }
+
+}  // namespace
+
+bool conv_tc_supported(const ConvArgs& a) {
+    if (a.in.fp32 || pick_bk(a.Cin) == 0) return false;
+    if (a.ks == 1) { if (a.stride != 1 || a.pad != 0) return false; }
+    else if (a.ks == 3) { if (a.pad != 1 || (a.stride != 1 && a.stride != 2)) return false; }
+    else return false;
+    if (a.in.pitch % 8 != 0 || (reinterpret_cast<uintptr_t>(a.in.ptr) & 15u)) return false;
+    if (a.out.pitch % 8 != 0 || (reinterpret_cast<uintptr_t>(a.out.ptr) & 15u)) return false;
+    if (!a.out.fp32 && a.Cout % 8 != 0) return false;
+    if (a.res && (a.res_pitch % 8 != 0 || (reinterpret_cast<uintptr_t>(a.res) & 15u))) return false;
+    if ((long long)a.B * a.out.H * a.out.W >= (1ll << 31)) return false;
+    return true;
+}
+
+int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
+    if (!conv_tc_supported(a)) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: unsupported convolution shape");
+    static EncodeTiledFn encode_tiled = nullptr;
+    static EncodeIm2colFn encode_im2col = nullptr;
+    if (!encode_tiled) {
+        int rc = driver_fn("cuTensorMapEncodeTiled", reinterpret_cast<void**>(&encode_tiled));
+        if (rc) return rc;
+        rc = driver_fn("cuTensorMapEncodeIm2col", reinterpret_cast<void**>(&encode_im2col));
+        if (rc) return rc;
+    }
+    ConvTcParams& p = launch->p;
+    const int BK = pick_bk(a.Cin);
+    int BN = a.Cout_pad < 128 ? a.Cout_pad : 128;
+    if (a.Cout_pad % BN != 0 || BN % 32 != 0)
+        return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: Cout_pad %d not tileable", a.Cout_pad);
+    const long long M = (long long)a.B * a.out.H * a.out.W;
+    p.out = a.out.ptr;
+    p.bias = a.bias;
+    p.res = a.res;
+    p.err_flag = err_flag;
+    p.out_pitch = a.out.pitch;
+    p.out_fp32 = a.out.fp32;
+    p.res_pitch = a.res_pitch;
+    p.M = (int)M;
+    p.Cout = a.Cout;
+    p.store_limit = a.out.fp32 ? (((a.Cout + 7) / 8 * 8) < a.out.pitch ? ((a.Cout + 7) / 8 * 8) : a.out.pitch)
+                               : a.Cout;
+    p.leaky = a.leaky;
+    p.ks = a.ks;
+    p.cchunks = a.Cin / BK;
+    p.BK = BK;
+    p.BN = BN;
+    p.Ho = a.out.H;
+    p.Wo = a.out.W;
+    p.stride = a.stride;
+    p.pad = a.pad;
+    int cols = 32;
+    while (cols < BN) cols <<= 1;
+    p.tmem_cols = cols;
+    // c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major both, N>>3 at 17, M>>4 at 24
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    const uint32_t stage_bytes = (uint32_t)(kBM + BN) * BK * 2;
+    int stages = (int)(98304u / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    launch->smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+    launch->grid = dim3((unsigned)((M + kBM - 1) / kBM), (unsigned)(a.Cout_pad / BN), 1);
+
+    // ---- A ----
+    const cuuint32_t estr1[4] = {1, 1, 1, 1};
+    CUresult r;
+    if (a.ks == 1) {
+        const cuuint64_t dims[2] = {(cuuint64_t)a.Cin, (cuuint64_t)M};
+        const cuuint64_t strides[1] = {(cuuint64_t)a.in.pitch * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)kBM};
+        r = encode_tiled(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.in.ptr, dims, strides, box, estr1,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        const cuuint64_t dims[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.in.W, (cuuint64_t)a.in.H, (cuuint64_t)a.B};
+        const cuuint64_t strides[3] = {(cuuint64_t)a.in.pitch * 2, (cuuint64_t)a.in.pitch * 2 * a.in.W,
+                                       (cuuint64_t)a.in.pitch * 2 * a.in.W * a.in.H};
+        // base pixel (the tap-(0,0) input position of an output pixel) ranges over
+        // [-pad, dim + pad - ks] in W and H
+        const int lower[2] = {-a.pad, -a.pad};
+        const int upper[2] = {a.pad - (a.ks - 1), a.pad - (a.ks - 1)};
+        const cuuint32_t estr[4] = {1, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1};
+        r = encode_im2col(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.in.ptr, dims, strides, lower, upper,
+                          (cuuint32_t)BK, (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swizzle_for(BK), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r == CUDA_SUCCESS && a.ks > 1 &&
+        (unsigned long long)a.in.pitch * 2ull * a.in.W * a.in.H * a.B < 131072ull) {
+        // im2col descriptors of tensors smaller than 128 KiB: drivers up to CUDA 13.1 set bit 21 of
+        // the second descriptor word, which must be clear (same fix-up CUTLASS applies)
+        reinterpret_cast<uint64_t*>(&p.tmA)[1] &= ~(1ull << 21);
+    }
+    if (r != CUDA_SUCCESS)
+        return fail(RTOD_ERR_CUDA, "cuTensorMapEncode (activations, ks=%d Cin=%d pitch=%d) failed: %d", a.ks,
+                    a.Cin, a.in.pitch, (int)r);
+    // ---- B ----
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.Cout_pad};
+        const cuuint64_t strides[1] = {(cuuint64_t)a.K * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+        r = encode_tiled(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.w), dims,
+                         strides, box, estr1, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK),
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+            return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (weights, K=%d Cout_pad=%d) failed: %d", a.K,
+                        a.Cout_pad, (int)r);
+    }
+    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)launch->smem_bytes > 200 * 1024 ? (int)launch->smem_bytes : 200 * 1024));
+    return RTOD_OK;
+}
+
+int conv_tc_launch(const ConvTcLaunch& launch, cudaStream_t stream) {
+    conv_tc_kernel<<<launch.grid, kThreads, launch.smem_bytes, stream>>>(launch.p);
+    RTOD_LAUNCH_OK("conv_tc_kernel");
+    return RTOD_OK;
+}
+
+}  // namespace rtod

@@ -1,0 +1,39 @@
+// conv_tc.cuh -- host interface of the tcgen05 implicit-GEMM convolution (conv_tc.cu)
+#pragma once
+#include <cuda.h>
+
+#include "layers.cuh"
+
+namespace rtod {
+
+// Everything one launch needs; built once at plan-bind time (the tensor maps embed addresses).
+struct alignas(64) ConvTcParams {
+    CUtensorMap tmA;            // activations: 2-D tiled {C, M} (1x1) or 4-D im2col {C, W, H, N} (3x3)
+    CUtensorMap tmB;            // weights: 2-D tiled {K, Cout_pad}
+    void* out;                  // NHWC bf16 (or fp32 head logits), pixel pitch out_pitch elements
+    const float* bias;          // [Cout_pad]
+    const __nv_bfloat16* res;   // shortcut operand or null
+    int* err_flag;              // device-side failure flag (pipeline time-out)
+    int out_pitch, out_fp32, res_pitch;
+    int M, Cout, store_limit;   // output pixels, real channels, channels actually stored
+    int leaky;
+    int ks, cchunks;            // kernel size, Cin / BK
+    int BK, BN, stages;         // K tile (16/32/64 -> 32B/64B/128B swizzle), N tile, pipeline depth
+    int Ho, Wo, stride, pad;    // im2col traversal
+    int tmem_cols;
+    uint32_t idesc;             // tcgen05 instruction descriptor (bf16 x bf16 -> fp32, M=128, N=BN)
+};
+
+struct ConvTcLaunch {           // host side: kernel parameters + launch geometry
+    ConvTcParams p;
+    dim3 grid;
+    uint32_t smem_bytes;
+};
+
+// true if the tensor-core kernel tiles this convolution
+bool conv_tc_supported(const ConvArgs& a);
+// fills `p` (encodes the TMA descriptors); `err_flag` is a device int
+int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch);
+int conv_tc_launch(const ConvTcLaunch& launch, cudaStream_t stream);
+
+}  // namespace rtod

@@ -1,0 +1,119 @@
+// decode.cu -- util.predict_transform (src/util.py:175-239) on the GPU.
+//
+// Two entry points share one element transform:
+//   * yolo_decode_nchw_kernel: the drop-in for predict_transform(): an NCHW fp32 head
+//     [B, A*(5+C), G, G] is transposed through shared memory (coalesced 128-byte reads along
+//     the cell axis, coalesced writes along the attribute axis) into [B, G*G*A, 5+C];
+//   * yolo_decode_heads_kernel: used inside the forward plan: the head convolutions leave
+//     their fp32 logits in NHWC (pixel-major) buffers, which is already the row order of
+//     the prediction tensor, so ONE launch decodes all yolo heads element-wise and writes
+//     the concatenated [B, N, 5+C] tensor (replaces predict_transform x3 + torch.cat x2,
+//     src/darknet.py:226-247).
+//
+// Exact op order of the reference: cx = (sigmoid(tx) + x) * stride;
+// w = (exp(tw) * f32(anchor_w / stride)) * stride; sigmoid on objectness and classes.
+#include "decode.cuh"
+
+namespace rtod {
+
+namespace {
+
+__device__ __forceinline__ float decode_value(float v, int attr, int cell_x, int cell_y, float aw,
+                                              float ah, float stride, int train) {
+    if (attr >= 4) return sigmoid_f32(v);
+    if (attr < 2) {
+        const float s = sigmoid_f32(v);
+        if (train) return s;
+        return __fmul_rn(__fadd_rn(s, (float)(attr == 0 ? cell_x : cell_y)), stride);
+    }
+    if (train) return v;
+    return __fmul_rn(__fmul_rn(expf(v), attr == 2 ? aw : ah), stride);
+}
+
+constexpr int kTileCells = 32;
+constexpr int kTileCh = 256;
+
+__global__ void __launch_bounds__(256)
+yolo_decode_nchw_kernel(const float* __restrict__ head, int G, int A, int L, float stride, int train,
+                        DecodeAnchors anchors, float* __restrict__ out) {
+    __shared__ float tile[kTileCh][kTileCells + 1];
+    const int GG = G * G, Ch = A * L;
+    const int cell0 = blockIdx.x * kTileCells, ch0 = blockIdx.z * kTileCh, b = blockIdx.y;
+    const int n_ch = min(kTileCh, Ch - ch0), n_cell = min(kTileCells, GG - cell0);
+    const float* src = head + ((long long)b * Ch + ch0) * GG + cell0;
+    for (int i = threadIdx.x; i < n_ch * kTileCells; i += 256) {
+        const int ch = i / kTileCells, cl = i % kTileCells;
+        tile[ch][cl] = cl < n_cell ? src[(long long)ch * GG + cl] : 0.0f;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < n_cell * n_ch; o += 256) {
+        const int cl = o / n_ch, chl = o % n_ch;
+        const int ch = ch0 + chl, cell = cell0 + cl;
+        const int a = ch / L, attr = ch % L;
+        const float v = decode_value(tile[chl][cl], attr, cell % G, cell / G, anchors.w[a],
+                                     anchors.h[a], stride, train);
+        out[((long long)b * GG + cell) * Ch + ch] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+yolo_decode_heads_kernel(DecodeHeads heads, int B, int N, int L, int train, float* __restrict__ pred) {
+    const long long total = (long long)B * N * L;
+    for (long long e = blockIdx.x * 256ll + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const int attr = (int)(e % L);
+        const long long br = e / L;
+        const int row = (int)(br % N), b = (int)(br / N);
+        int h = 0;
+#pragma unroll
+        for (int k = 1; k < kMaxHeads; ++k)
+            if (k < heads.count && row >= heads.row_base[k]) h = k;
+        const int local = row - heads.row_base[h];
+        const int A = heads.num_anchors[h], G = heads.grid[h];
+        const int cell = local / A, a = local % A;
+        const float v = heads.raw[h][((long long)b * G * G + cell) * heads.pitch[h] + a * L + attr];
+        pred[e] = decode_value(v, attr, cell % G, cell / G, heads.anchor_w[h][a], heads.anchor_h[h][a],
+                               heads.stride[h], train);
+    }
+}
+
+}  // namespace
+
+int launch_decode_heads(const DecodeHeads& heads, int B, int N, int L, int train, float* pred,
+                        cudaStream_t stream) {
+    const long long total = (long long)B * N * L;
+    if (total == 0) return RTOD_OK;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)kNumSMs * 32) blocks = (long long)kNumSMs * 32;
+    yolo_decode_heads_kernel<<<(unsigned)blocks, 256, 0, stream>>>(heads, B, N, L, train, pred);
+    RTOD_LAUNCH_OK("yolo_decode_heads_kernel");
+    return RTOD_OK;
+}
+
+}  // namespace rtod
+
+using namespace rtod;
+
+extern "C" int rtod_yolo_decode(const float* head_nchw, int B, int G, int A, int C, int inp_dim,
+                                const float* anchors_host, int train, float* out, void* stream_) {
+    if (B < 0 || G <= 0 || A <= 0 || A > RTOD_MAX_ANCHORS || C < 0 || inp_dim <= 0)
+        return fail(RTOD_ERR_BAD_ARG, "rtod_yolo_decode: bad shape B=%d G=%d A=%d C=%d inp_dim=%d", B, G,
+                    A, C, inp_dim);
+    if (B == 0) return RTOD_OK;
+    if (!head_nchw || !out || !anchors_host)
+        return fail(RTOD_ERR_BAD_ARG, "rtod_yolo_decode: null pointer");
+    const int stride = inp_dim / G;                       // src/util.py:194
+    if (stride <= 0 || inp_dim / stride != G)             // src/util.py:195 grid_size must match
+        return fail(RTOD_ERR_BAD_ARG, "rtod_yolo_decode: inp_dim %d does not fit grid %d", inp_dim, G);
+    DecodeAnchors anc;
+    for (int a = 0; a < RTOD_MAX_ANCHORS; ++a) {
+        // python evaluates anchor/stride in double and FloatTensor() rounds it to fp32
+        anc.w[a] = a < A ? (float)((double)anchors_host[2 * a] / (double)stride) : 0.0f;
+        anc.h[a] = a < A ? (float)((double)anchors_host[2 * a + 1] / (double)stride) : 0.0f;
+    }
+    const int L = 5 + C, Ch = A * L, GG = G * G;
+    dim3 grid(ceil_div(GG, kTileCells), B, ceil_div(Ch, kTileCh));
+    yolo_decode_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(head_nchw, G, A, L, (float)stride,
+                                                                    train, anc, out);
+    RTOD_LAUNCH_OK("yolo_decode_nchw_kernel");
+    return RTOD_OK;
+}

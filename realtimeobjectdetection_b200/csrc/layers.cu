@@ -1,0 +1,323 @@
+// layers.cu -- the non-GEMM layers of Darknet.forward (src/darknet.py:199-295) on NHWC bf16
+// activations: stem convolution (Cin = 3, fused NCHW fp32 -> NHWC bf16), max-pool
+// (src/darknet.py:17-46, 547-555), bilinear x2 upsample (src/darknet.py:591-592), the
+// copy/add fall-backs for route/shortcut (src/darknet.py:263-290) when they cannot be fused
+// into a convolution, and the weight ingest (BatchNorm fold + K-major bf16 re-layout,
+// src/darknet.py:316-410).  All of them are HBM-bound: 16-byte vector accesses, one pass.
+#include "layers.cuh"
+
+namespace rtod {
+
+namespace {
+
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// ---------------------------------------------------------------------------------------------
+// stem: 3x3 convolution over a 3-channel NCHW fp32 image, bias + leaky fused, NHWC bf16 out
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+stem_conv3x3_kernel(const float* __restrict__ x, int B, int H, int W, const float* __restrict__ w,
+                    const float* __restrict__ bias, int Cout, int stride, int pad, int leaky, Act out) {
+    extern __shared__ float stem_w[];                     // [Cout][27] then [Cout] bias
+    for (int i = threadIdx.x; i < Cout * 27; i += 128) stem_w[i] = w[i];
+    for (int i = threadIdx.x; i < Cout; i += 128) stem_w[Cout * 27 + i] = bias[i];
+    __syncthreads();
+    const int Ho = out.H, Wo = out.W;
+    const long long pix = blockIdx.x * 128ll + threadIdx.x;
+    if (pix >= (long long)B * Ho * Wo) return;
+    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+    float in[27];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+                in[(c * 3 + ky) * 3 + kx] =
+                    (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                        ? __ldg(x + (((long long)b * 3 + c) * H + iy) * W + ix)
+                        : 0.0f;
+            }
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out.ptr) + pix * out.pitch;
+    for (int n0 = 0; n0 < Cout; n0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = stem_w[Cout * 27 + n0 + j];
+#pragma unroll
+        for (int k = 0; k < 27; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(in[k], stem_w[(n0 + j) * 27 + k], acc[j]);
+        if (leaky)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = leaky01(acc[j]);
+        uint4 v;
+        v.x = pack_bf16x2(acc[0], acc[1]);
+        v.y = pack_bf16x2(acc[2], acc[3]);
+        v.z = pack_bf16x2(acc[4], acc[5]);
+        v.w = pack_bf16x2(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(dst + n0) = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout converters (plan input when the first layer is not a stem; debug read-back)
+// ---------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, Act out) {
+    const int HW = out.H * out.W, groups = out.C / 8;
+    const long long total = (long long)B * HW * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i % HW);
+        const int g = (int)((i / HW) % groups);
+        const int b = (int)(i / ((long long)HW * groups));
+        const float* src = x + ((long long)b * out.C + g * 8) * HW + p;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (long long)j * HW);
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]);
+        o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]);
+        o.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out.ptr) +
+                                  ((long long)b * HW + p) * out.pitch + g * 8) = o;
+    }
+}
+
+__global__ void nhwc_to_nchw_kernel(Act in, int B, float* __restrict__ out) {
+    const int HW = in.H * in.W;
+    const long long total = (long long)B * in.C * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i % HW);
+        const int c = (int)((i / HW) % in.C);
+        const int b = (int)(i / ((long long)HW * in.C));
+        const long long src = ((long long)b * HW + p) * in.pitch + c;
+        out[i] = in.fp32 ? reinterpret_cast<const float*>(in.ptr)[src]
+                         : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in.ptr)[src]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// max-pool: MaxPool2d(size, stride) (floor mode, no padding) or, for stride 1, the reference's
+// MaxPoolStride1: replicate-pad right/bottom by size-1, then pool with stride size-1
+// ---------------------------------------------------------------------------------------------
+__global__ void maxpool_kernel(Act in, Act out, int B, int size, int step, int clamp_edge) {
+    const int groups = out.C / 8;
+    const long long total = (long long)B * out.H * out.W * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % groups);
+        const int ox = (int)((i / groups) % out.W);
+        const int oy = (int)((i / ((long long)groups * out.W)) % out.H);
+        const int b = (int)(i / ((long long)groups * out.W * out.H));
+        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(in.ptr) + g * 8;
+        __nv_bfloat162 best[4];
+        bool first = true;
+        for (int dy = 0; dy < size; ++dy) {
+            int iy = oy * step + dy;
+            if (iy >= in.H) {
+                if (!clamp_edge) continue;
+                iy = in.H - 1;
+            }
+            for (int dx = 0; dx < size; ++dx) {
+                int ix = ox * step + dx;
+                if (ix >= in.W) {
+                    if (!clamp_edge) continue;
+                    ix = in.W - 1;
+                }
+                const uint4 v = ldg16(base + (((long long)b * in.H + iy) * in.W + ix) * in.pitch);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+                if (first) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) best[j] = h[j];
+                    first = false;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) best[j] = __hmax2(best[j], h[j]);
+                }
+            }
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out.ptr) +
+                                  (((long long)b * out.H + oy) * out.W + ox) * out.pitch + g * 8) =
+            *reinterpret_cast<uint4*>(best);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bilinear x2, align_corners=False: even rows .25/.75 of (i-1, i), odd rows .75/.25 of (i, i+1),
+// indices clamped at the border; evaluated like ATen: h0*(w0*a + w1*b) + h1*(w0*c + w1*d)
+// ---------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(Act in, Act out, int B) {
+    const int groups = out.C / 8;
+    const long long total = (long long)B * out.H * out.W * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % groups);
+        const int ox = (int)((i / groups) % out.W);
+        const int oy = (int)((i / ((long long)groups * out.W)) % out.H);
+        const int b = (int)(i / ((long long)groups * out.W * out.H));
+        const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.0f), sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.0f);
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int y1 = min(y0 + 1, in.H - 1), x1 = min(x0 + 1, in.W - 1);
+        const float hy1 = sy - y0, hy0 = 1.0f - hy1, wx1 = sx - x0, wx0 = 1.0f - wx1;
+        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(in.ptr) + g * 8;
+        const long long row0 = ((long long)b * in.H + y0) * in.W, row1 = ((long long)b * in.H + y1) * in.W;
+        const uint4 a = ldg16(base + (row0 + x0) * in.pitch), bb = ldg16(base + (row0 + x1) * in.pitch);
+        const uint4 c = ldg16(base + (row1 + x0) * in.pitch), d = ldg16(base + (row1 + x1) * in.pitch);
+        const uint32_t* pa = &a.x; const uint32_t* pb = &bb.x; const uint32_t* pc = &c.x; const uint32_t* pd = &d.x;
+        uint4 o;
+        uint32_t* po = &o.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float lo = hy0 * (wx0 * bf16_lo(pa[j]) + wx1 * bf16_lo(pb[j])) +
+                             hy1 * (wx0 * bf16_lo(pc[j]) + wx1 * bf16_lo(pd[j]));
+            const float hi = hy0 * (wx0 * bf16_hi(pa[j]) + wx1 * bf16_hi(pb[j])) +
+                             hy1 * (wx0 * bf16_hi(pc[j]) + wx1 * bf16_hi(pd[j]));
+            po[j] = pack_bf16x2(lo, hi);
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out.ptr) +
+                                  (((long long)b * out.H + oy) * out.W + ox) * out.pitch + g * 8) = o;
+    }
+}
+
+__global__ void copy_kernel(Act in, Act out, int B) {
+    const int groups = out.C / 8;
+    const long long total = (long long)B * out.H * out.W * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % groups);
+        const long long p = i / groups;
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out.ptr) + p * out.pitch + g * 8) =
+            ldg16(reinterpret_cast<const __nv_bfloat16*>(in.ptr) + p * in.pitch + g * 8);
+    }
+}
+
+__global__ void add_kernel(Act a, Act b, Act out, int B) {
+    const int groups = out.C / 8;
+    const long long total = (long long)B * out.H * out.W * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % groups);
+        const long long p = i / groups;
+        const uint4 va = ldg16(reinterpret_cast<const __nv_bfloat16*>(a.ptr) + p * a.pitch + g * 8);
+        const uint4 vb = ldg16(reinterpret_cast<const __nv_bfloat16*>(b.ptr) + p * b.pitch + g * 8);
+        const uint32_t* pa = &va.x; const uint32_t* pb = &vb.x;
+        uint4 o;
+        uint32_t* po = &o.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            po[j] = pack_bf16x2(bf16_lo(pa[j]) + bf16_lo(pb[j]), bf16_hi(pa[j]) + bf16_hi(pb[j]));
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out.ptr) + p * out.pitch + g * 8) = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight ingest: BatchNorm fold (eval semantics) + [Cout,Cin,k,k] fp32 -> [Cout][(ky,kx,c)] bf16
+// ---------------------------------------------------------------------------------------------
+__global__ void fold_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ mean, const float* __restrict__ var,
+                                 float eps, int Cout, int Cin, int ks, __nv_bfloat16* __restrict__ wp,
+                                 float* __restrict__ wf, float* __restrict__ bias_out) {
+    const int K = Cin * ks * ks;
+    const long long total = (long long)Cout * K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(i / K), r = (int)(i % K);        // r indexes [c][ky][kx]
+        const int c = r / (ks * ks), t = r % (ks * ks);
+        const float scale = gamma ? gamma[o] * (1.0f / sqrtf(var[o] + eps)) : 1.0f;
+        const float v = w[i] * scale;
+        wp[(long long)o * K + (long long)t * Cin + c] = __float2bfloat16_rn(v);
+        if (wf) wf[i] = v;
+        if (r == 0) {
+            float bv = bias ? bias[o] : 0.0f;
+            if (gamma) bv = (bv - mean[o]) * scale + beta[o];
+            bias_out[o] = bv;
+        }
+    }
+}
+
+int grid_for(long long total, int threads) {
+    long long blocks = (total + threads - 1) / threads;
+    const long long cap = (long long)kNumSMs * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+
+int launch_stem_conv(const float* x, int B, int Cin, int H, int W, const float* w, const float* bias,
+                     int Cout, int ks, int stride, int pad, int leaky, Act out, cudaStream_t stream) {
+    if (Cin != 3 || ks != 3 || Cout % 8 != 0 || Cout > 256 || out.fp32)
+        return fail(RTOD_ERR_UNSUPPORTED, "stem conv supports 3x3, Cin=3, Cout%%8==0, Cout<=256");
+    const long long pixels = (long long)B * out.H * out.W;
+    stem_conv3x3_kernel<<<ceil_div(pixels, 128), 128, (size_t)Cout * 28 * sizeof(float), stream>>>(
+        x, B, H, W, w, bias, Cout, stride, pad, leaky, out);
+    RTOD_LAUNCH_OK("stem_conv3x3_kernel");
+    return RTOD_OK;
+}
+
+int launch_nchw_to_nhwc(const float* x, int B, Act out, cudaStream_t stream) {
+    if (out.C % 8 != 0 || out.fp32) return fail(RTOD_ERR_UNSUPPORTED, "input channels must be a multiple of 8");
+    const long long total = (long long)B * out.H * out.W * (out.C / 8);
+    nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, B, out);
+    RTOD_LAUNCH_OK("nchw_to_nhwc_kernel");
+    return RTOD_OK;
+}
+
+int launch_nhwc_to_nchw(Act in, int B, float* out, cudaStream_t stream) {
+    const long long total = (long long)B * in.C * in.H * in.W;
+    nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, B, out);
+    RTOD_LAUNCH_OK("nhwc_to_nchw_kernel");
+    return RTOD_OK;
+}
+
+int launch_maxpool(Act in, Act out, int B, int size, int stride, cudaStream_t stream) {
+    if (in.C % 8 != 0 || in.fp32 || out.fp32) return fail(RTOD_ERR_UNSUPPORTED, "maxpool needs bf16, C%%8==0");
+    const long long total = (long long)B * out.H * out.W * (out.C / 8);
+    const int step = stride != 1 ? stride : size - 1;           // src/darknet.py:35,45
+    maxpool_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, out, B, size, step < 1 ? 1 : step,
+                                                             stride == 1);
+    RTOD_LAUNCH_OK("maxpool_kernel");
+    return RTOD_OK;
+}
+
+int launch_upsample2x(Act in, Act out, int B, cudaStream_t stream) {
+    if (in.C % 8 != 0 || in.fp32 || out.fp32) return fail(RTOD_ERR_UNSUPPORTED, "upsample needs bf16, C%%8==0");
+    const long long total = (long long)B * out.H * out.W * (out.C / 8);
+    upsample2x_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, out, B);
+    RTOD_LAUNCH_OK("upsample2x_kernel");
+    return RTOD_OK;
+}
+
+int launch_copy(Act in, Act out, int B, cudaStream_t stream) {
+    if (in.C % 8 != 0 || in.fp32 || out.fp32) return fail(RTOD_ERR_UNSUPPORTED, "copy needs bf16, C%%8==0");
+    const long long total = (long long)B * out.H * out.W * (out.C / 8);
+    copy_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, out, B);
+    RTOD_LAUNCH_OK("copy_kernel");
+    return RTOD_OK;
+}
+
+int launch_add(Act a, Act b, Act out, int B, cudaStream_t stream) {
+    if (out.C % 8 != 0 || a.fp32 || b.fp32 || out.fp32)
+        return fail(RTOD_ERR_UNSUPPORTED, "shortcut add needs bf16, C%%8==0");
+    const long long total = (long long)B * out.H * out.W * (out.C / 8);
+    add_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a, b, out, B);
+    RTOD_LAUNCH_OK("add_kernel");
+    return RTOD_OK;
+}
+
+int launch_fold_pack(const float* w, const float* bias, const float* gamma, const float* beta,
+                     const float* mean, const float* var, float eps, int Cout, int Cin, int ks,
+                     __nv_bfloat16* wp, float* wf, float* bias_out, cudaStream_t stream) {
+    const long long total = (long long)Cout * Cin * ks * ks;
+    fold_pack_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, bias, gamma, beta, mean, var, eps,
+                                                               Cout, Cin, ks, wp, wf, bias_out);
+    RTOD_LAUNCH_OK("fold_pack_kernel");
+    return RTOD_OK;
+}
+
+}  // namespace rtod

@@ -1,0 +1,43 @@
+// layers.cuh -- activation views and launchers of the non-GEMM layer kernels (layers.cu) and the
+// two convolution back ends (conv_tc.cu = tcgen05 implicit GEMM, conv_simt.cu = validation).
+#pragma once
+#include "common.cuh"
+
+namespace rtod {
+
+// NHWC activation view.  `ptr` points at channel 0 of the view's channel slice inside a buffer
+// whose pixels are `pitch` elements apart (pitch > C when the view is a slice of a route/concat
+// buffer).  Elements are bf16, or fp32 for detection-head logits.
+struct Act {
+    void* ptr;
+    int C, pitch, H, W;
+    int fp32;
+};
+
+struct ConvArgs {
+    Act in, out;
+    const __nv_bfloat16* w;     // [Cout_pad][K] K-major bf16, K = (ky*ks + kx)*Cin + c, BN folded
+    const float* bias;          // [Cout_pad] fp32 (BN folded)
+    const __nv_bfloat16* res;   // optional shortcut operand, same pixels/channels as out
+    int res_pitch;
+    int B, Cin, Cout, Cout_pad, ks, stride, pad, leaky;
+    int K;                      // ks*ks*Cin
+};
+
+int launch_stem_conv(const float* x_nchw, int B, int Cin, int H, int W, const float* w_f32,
+                     const float* bias, int Cout, int ks, int stride, int pad, int leaky, Act out,
+                     cudaStream_t stream);
+int launch_nchw_to_nhwc(const float* x_nchw, int B, Act out, cudaStream_t stream);
+int launch_nhwc_to_nchw(Act in, int B, float* out_nchw, cudaStream_t stream);
+int launch_maxpool(Act in, Act out, int B, int size, int stride, cudaStream_t stream);
+int launch_upsample2x(Act in, Act out, int B, cudaStream_t stream);
+int launch_copy(Act in, Act out, int B, cudaStream_t stream);
+int launch_add(Act a, Act b, Act out, int B, cudaStream_t stream);
+// BN fold + K-major bf16 re-layout (and the fp32 [Cout][Cin*ks*ks] copy the stem kernel reads)
+int launch_fold_pack(const float* w, const float* bias, const float* gamma, const float* beta,
+                     const float* mean, const float* var, float eps, int Cout, int Cin, int ks,
+                     __nv_bfloat16* w_packed, float* w_f32_or_null, float* bias_out,
+                     cudaStream_t stream);
+int launch_conv_simt(const ConvArgs& a, cudaStream_t stream);
+
+}  // namespace rtod

@@ -1,0 +1,151 @@
+"""Detection utilities: drop-in mirror of the reference's ``src/util.py`` hot-path functions.
+
+Same names, argument order, defaults and return conventions as the reference
+(``predict_transform`` src/util.py:175-239, ``write_results`` :242-346, ``bbox_iou``
+:120-153, ``confidence_mask`` :106-117); the arithmetic runs in the sm_100a kernels of
+``librtod.so`` through its C ABI.  Inputs are never modified, outputs are fresh tensors.
+
+Tensors that live on the host are staged to the current CUDA device (pinned, asynchronous
+where possible) and the result is returned on the device the input came from -- there is
+no CPU implementation here.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+_WORKSPACES: dict = {}
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("realtimeobjectdetection_b200 needs a CUDA device (B200, sm_100a); "
+                           "there is no CPU fallback")
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _to_device(t: torch.Tensor):
+    """fp32 contiguous CUDA view/copy of ``t`` plus the device results should return to."""
+    home = t.device
+    if t.is_cuda:
+        dev = t.device
+    else:
+        _require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device())
+    t = t.detach()
+    if t.dtype != torch.float32 or not t.is_cuda:
+        t = t.to(device=dev, dtype=torch.float32, non_blocking=True)
+    return t.contiguous(), dev, home
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    key = (device.type, device.index)
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = buf
+    return buf
+
+
+def confidence_mask(tensor: torch.Tensor, confidence: float) -> torch.Tensor:
+    """``tensor * (tensor[:, :, 4] > confidence)`` -- src/util.py:106-117."""
+    lib = _lib.load()
+    x, dev, home = _to_device(tensor)
+    out = torch.empty_like(x)
+    rows = x.numel() // x.shape[-1] if x.numel() else 0
+    with torch.cuda.device(dev):
+        _lib.check(lib.rtod_confidence_mask(x.data_ptr(), rows, x.shape[-1], float(confidence),
+                                            out.data_ptr(), _stream_ptr(dev)))
+    return out.to(home)
+
+
+def bbox_iou(box1: torch.Tensor, box2: torch.Tensor) -> torch.Tensor:
+    """Broadcasting IoU with the +1 pixel convention -- src/util.py:120-153."""
+    lib = _lib.load()
+    home = box1.device
+    a, dev, _ = _to_device(box1)
+    b = box2.detach().to(device=dev, dtype=torch.float32)
+    lead = torch.broadcast_shapes(a.shape[:-1], b.shape[:-1])
+    n_out = 1
+    for s in lead:
+        n_out *= s
+    out = torch.empty(lead, dtype=torch.float32, device=dev)
+    if n_out == 0:
+        return out.to(home)
+
+    def flat(t):
+        n = t.numel() // t.shape[-1]
+        if n == 1 or n == n_out:
+            return t.contiguous().view(n, t.shape[-1]), n
+        t = t.expand(*lead, t.shape[-1]).contiguous()
+        return t.view(n_out, t.shape[-1]), n_out
+
+    a2, n1 = flat(a)
+    b2, n2 = flat(b)
+    with torch.cuda.device(dev):
+        _lib.check(lib.rtod_bbox_iou(a2.data_ptr(), n1, a2.shape[1], b2.data_ptr(), n2, b2.shape[1],
+                                     out.data_ptr(), _stream_ptr(dev)))
+    return out.to(home)
+
+
+def predict_transform(prediction, inp_dim, anchors, num_class, CUDA, TRAIN=False) -> torch.Tensor:
+    """One YOLO head, NCHW ``[B, A*(5+C), G, G]`` -> ``[B, G*G*A, 5+C]`` -- src/util.py:175-239.
+
+    ``CUDA`` is accepted for signature compatibility; the computation is always on the GPU.
+    """
+    lib = _lib.load()
+    x, dev, home = _to_device(prediction)
+    if x.dim() != 4 or x.size(2) != x.size(3):
+        raise ValueError("predict_transform expects [B, A*(5+C), G, G], got %s" % (tuple(x.shape),))
+    batch, grid = x.size(0), x.size(2)
+    n_anchor, attrs = len(anchors), 5 + int(num_class)
+    if x.size(1) != n_anchor * attrs:
+        raise RuntimeError("shape '[%d, %d, %d]' is invalid for input of size %d"
+                           % (batch, attrs * n_anchor, grid * grid, x.numel()))
+    flat = (ctypes.c_float * (2 * n_anchor))(*[float(v) for pair in anchors for v in pair[:2]])
+    out = torch.empty(batch, grid * grid * n_anchor, attrs, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.rtod_yolo_decode(x.data_ptr(), batch, grid, n_anchor, int(num_class), int(inp_dim),
+                                        flat, int(bool(TRAIN)), out.data_ptr(), _stream_ptr(dev)))
+    return out.to(home)
+
+
+def write_results(prediction, num_class, confidence=0.6, nms_conf=0.4):
+    """Threshold + per-image per-class greedy NMS -- src/util.py:242-346.
+
+    Returns ``[D, 8]`` fp32 rows ``[img, x1, y1, x2, y2, obj, cls_conf, cls]`` ordered image,
+    class ascending, objectness descending -- or the int ``0`` when nothing survives (callers
+    test ``type(x) == int``).  Rows of one (image, class) with bit-equal objectness are ordered
+    by row index (the reference's ``torch.sort`` leaves that order unspecified).
+    """
+    lib = _lib.load()
+    x, dev, home = _to_device(prediction)
+    if x.dim() != 3 or x.size(2) < 5 + int(num_class):
+        raise ValueError("write_results expects [B, N, >=5+num_class], got %s" % (tuple(x.shape),))
+    if x.size(2) != 5 + int(num_class):
+        x = x[:, :, :5 + int(num_class)].contiguous()      # reference slices 5:5+num_class (:279)
+    B, N, C = x.size(0), x.size(1), int(num_class)
+    if B == 0 or N == 0:
+        return 0
+    nbytes = lib.rtod_write_results_workspace_bytes(B, N, C)
+    ws = _workspace(dev, nbytes + 256)
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    cap = B * N
+    rows = torch.empty(cap, 8, dtype=torch.float32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.rtod_write_results(x.data_ptr(), B, N, C, float(confidence), float(nms_conf),
+                                          rows.data_ptr(), cap, count.data_ptr(), ws_ptr, nbytes,
+                                          _stream_ptr(dev)))
+    d = int(count.item())                                   # the one host sync of the call
+    if d == 0:
+        return 0
+    if d > cap:
+        raise RuntimeError("write_results: %d detections exceed capacity %d" % (d, cap))
+    return rows[:d].clone().to(home)
