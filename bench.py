@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- YOLOv3-416 frames/s (forward + decode + NMS), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one pass of the hot path over one batch of synthetic frames per rank:
+``Darknet.forward`` (tcgen05 convolutions + fused decode) followed by ``write_results``
+(threshold + per-class NMS), 80 classes, conf 0.5 / nms 0.4, YOLOv3 (cfg/yolov3.cfg) at
+416x416.  Weights are synthetic (``synth.synth_stream(seed 0, "calibrated")``: random
+BN-calibrated network whose objectness passes 0.5 for about 1 % of the rows), written as a
+Darknet ``.weights`` file and ingested through ``load_weights`` like real ones.
+
+value   whole-job frames/s with the frames already resident in HBM (CUDA events, barrier + sync
+        on both sides, max over ranks).
+e2e     the same metric through the public API with HOST buffers: pinned fp32 frames are copied
+        host->device inside the timed region (DetectionPipeline: side-stream copies overlap the
+        previous batch) and every step's detections are read back to the host.
+roofline  the dominant kernel (conv_tc_kernel, tensor bound): sum of 2*M*N*K over its launches
+        divided by the sum of their device times, measured per layer with CUDA events by
+        rtod_plan_forward_profile inside this run; peak = MEASURED_PEAKS.json.
+cpu_baseline  the oracle port (PyTorch CPU ops, eval-mode BN) on the host cores, bounded sample.
+--impl reference  times that CPU port as the reference arm (the reference is Python and cannot
+        travel to the GPU box; oracle/ is its validated restatement), batch 1 per call like
+        detect.py:27.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+METRIC = "YOLOv3-416 frames/s (fwd+decode+NMS)"
+RESO, CLASSES, CONF, NMS = 416, 80, 0.5, 0.4
+FRAME_GFLOP = 65.864                      # conv FLOPs per 416x416 frame
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cfg", default="yolov3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"],
+                "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def synthetic_weights_file(cfg_name, seed=0):
+    from realtimeobjectdetection_b200 import synth
+    from realtimeobjectdetection_b200.cfg import builtin_cfg, parse_cfg
+    cfg = builtin_cfg(cfg_name)
+    blocks = parse_cfg(cfg)
+    stream = synth.synth_stream(blocks, seed, "calibrated")
+    path = os.path.join(tempfile.gettempdir(), "rtod_bench_%s_%d_%d.weights" % (cfg_name, seed, os.getpid()))
+    synth.write_weights_file(path, stream)
+    return cfg, blocks, stream, path
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            f = [v.strip() for v in line.split(",")]
+            if len(f) < 8 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sample in timed region"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ reference / CPU arm
+def cpu_port_frames_per_s(cfg, stream, blocks, frames, reps, batch_per_call, warmup):
+    """oracle port (eval-mode BN) + oracle write_results on the host cores"""
+    import oracle
+    from realtimeobjectdetection_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    state = {k: torch.from_numpy(v) for k, v in synth.stream_to_state(blocks, stream).items()}
+    port = oracle.DarknetPort(cfg, state)
+    port.net_info["height"] = RESO
+    x = torch.from_numpy(np.random.RandomState(1).rand(frames, 3, RESO, RESO).astype(np.float32))
+
+    def one_pass():
+        dets = 0
+        with torch.no_grad():
+            for lo in range(0, frames, batch_per_call):
+                pred = port(x[lo:lo + batch_per_call])
+                out = oracle.write_results(pred, CLASSES, CONF, NMS)
+                dets += 0 if isinstance(out, int) else out.size(0)
+        return dets
+
+    for _ in range(warmup):
+        one_pass()
+    times = []
+    for _ in range(reps):
+        t = time.perf_counter()
+        one_pass()
+        times.append(time.perf_counter() - t)
+    return frames / statistics.median(times), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, blocks, stream, wpath = synthetic_weights_file(args.cfg)
+    os.remove(wpath)
+    frames_per_step = 2
+    t0 = time.perf_counter()
+    fps, times = cpu_port_frames_per_s(cfg, stream, blocks, frames_per_step, args.steps, 1, args.warmup)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": statistics.median(times) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "yolov3.cfg 416x416, 80 classes, conf 0.5 / nms 0.4, CPU (CUDA=False), "
+                               "batch 1 per call as detect.py:27, %d frames per step" % frames_per_step,
+                   "weights": "synthetic calibrated seed 0", "bn": "eval (running statistics)"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": "%d steps x %d frames, oracle port of src/darknet.py + src/util.py (PyTorch %s CPU)"
+                                   % (args.steps, frames_per_step, torch.__version__)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+    from realtimeobjectdetection_b200 import Darknet, _lib, write_results
+    from realtimeobjectdetection_b200.pipeline import DetectionPipeline
+    from realtimeobjectdetection_b200.sharding import gather_detections
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    cfg, blocks, stream, wpath = synthetic_weights_file(args.cfg)
+    model = Darknet(cfg, True)
+    model.load_weights(wpath)                     # the reference's ingest path (src/darknet.py:316)
+    os.remove(wpath)
+    model.net_info["height"] = RESO
+    model.eval()
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    frames = [torch.rand(B, 3, RESO, RESO, device=dev, generator=gen) for _ in range(2)]   # 2 x 133 MB @ B=64
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        pred = model(frames[i & 1])
+        det = write_results(pred, CLASSES, CONF, NMS)
+        if world > 1:
+            det = gather_detections(det, rank * B)       # rows to rank 0 (NCCL), img index made global
+        return det
+
+    n_det = 0
+    for i in range(W):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for i in range(K):
+        det = step(i)
+        if rank == 0 and not isinstance(det, int) and det is not None:
+            n_det += det.size(0)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop(t0, t1)
+    value = world * B * K / (ms_total / 1e3)
+    model.check_device()
+
+    # ---- e2e: host buffers, H2D inside the timed region, detections read back ------------------
+    host = [torch.rand(B, 3, RESO, RESO).pin_memory() for _ in range(2)]
+    pipe = DetectionPipeline(model, CLASSES, CONF, NMS, device=dev)
+    for _ in pipe.run(host[i & 1] for i in range(W)):
+        pass
+    pipe.h2d_bytes = pipe.d2h_bytes = 0
+    barrier()
+    e0.record()
+    for det in pipe.run(host[i & 1] for i in range(K)):
+        if world > 1:
+            gather_detections(det if isinstance(det, int) else det.to(dev), rank * B)
+    e1.record()
+    barrier()
+    ms_e = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (float(ms_e.item()) / 1e3)
+    e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes // K,
+           "d2h_bytes_per_step": pipe.d2h_bytes // K, "ms_per_step": float(ms_e.item()) / K,
+           "api": "DetectionPipeline(model).run(pinned host batches) -> Darknet.forward + write_results -> .cpu()"}
+
+    # ---- roofline of the dominant kernel, measured live per layer --------------------------------
+    peaks = measured_peaks()
+    plan = next(reversed(model._plans.values()))
+    n_layers = len(blocks) - 1
+    ms_arr = (ctypes.c_float * (n_layers + 1))()
+    kind_arr = (ctypes.c_int * n_layers)()
+    pred_buf = torch.empty(B, plan.n_rows, plan.n_attrs, device=dev)
+    tc_ms, tc_flops, per_layer = 0.0, 0.0, []
+    reps = 3
+    for r in range(reps + 1):
+        _lib.check(lib.rtod_plan_forward_profile(plan.handle, frames[r & 1].data_ptr(), pred_buf.data_ptr(), 0,
+                                                 torch.cuda.current_stream(dev).cuda_stream, ms_arr, kind_arr))
+        if r == 0:
+            continue                                   # warm-up pass of the profiled (non-graph) path
+        for i in range(n_layers):
+            if kind_arr[i] == 1:
+                tc_ms += ms_arr[i]
+                tc_flops += lib.rtod_plan_layer_flops(plan.handle, i)
+    fwd_ms = sum(ms_arr[i] for i in range(n_layers + 1))
+    for i in range(n_layers):
+        if kind_arr[i]:
+            per_layer.append((i, int(kind_arr[i]), round(float(ms_arr[i]), 4),
+                              round(lib.rtod_plan_layer_flops(plan.handle, i) / max(ms_arr[i], 1e-6) / 1e9, 1)))
+    n_tc = sum(1 for i in range(n_layers) if kind_arr[i] == 1)
+    achieved = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": achieved,
+                "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s): kernel timed inside a long step"
+                               % peaks["source"],
+                "launches_per_step": n_tc, "flops_per_step": tc_flops / reps,
+                "avg_launch_ms": tc_ms / reps / max(n_tc, 1), "share_of_forward": tc_ms / reps / fwd_ms}
+
+    # NMS stage (HBM bound): device time of rtod_write_results on this step's prediction tensor
+    pred = model(frames[0])
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        write_results(pred, CLASSES, CONF, NMS)
+    e1.record()
+    torch.cuda.synchronize()
+    nms_ms = e0.elapsed_time(e1) / 5
+    nms_bytes = pred.numel() * 4
+    roofline_nms = {"bound": "hbm", "kernel": "nms_scan+nms_image+nms_emit (write_results call)",
+                    "achieved": nms_bytes / nms_ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": nms_bytes / nms_ms / 1e6 / peaks["hbm_gbs"], "traffic": None, "ms": nms_ms}
+
+    # ---- p50 batch-1 latency (BASELINE configs[1]) ---------------------------------------------------
+    latency = None
+    if not args.no_latency and rank == 0:
+        x1 = torch.rand(1, 3, RESO, RESO, device=dev)
+        for _ in range(20):
+            write_results(model(x1), CLASSES, CONF, NMS)
+        lat = []
+        for _ in range(200):
+            e0.record()
+            write_results(model(x1), CLASSES, CONF, NMS)
+            e1.record()
+            e1.synchronize()
+            lat.append(e0.elapsed_time(e1))
+        latency = {"p50_ms": statistics.median(lat), "p99_ms": sorted(lat)[197], "batch": 1,
+                   "what": "Darknet.forward + write_results, frame resident in HBM, CUDA events"}
+
+    # ---- CPU baseline (rank 0, N=1 only; bounded sample) ------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        fps, times = cpu_port_frames_per_s(cfg, stream, blocks, 4, 3, 4, 1)
+        cpu = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "4 frames (one batch of 4) x 3 reps + 1 warm-up, oracle port, eval-mode BN, %.1f s"
+                         % sum(times)}
+
+    if rank == 0:
+        launches_per_step = plan.launches + 3 + (1 if world > 1 else 0)
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "yolov3.cfg 416x416 forward+decode+NMS, 80 classes, conf 0.5 / nms 0.4, "
+                                   "batch %d per GPU" % B,
+                       "global_batch": world * B, "parallelism": "frames sharded, dp%d, no collective on the hot "
+                                                                 "path; detections gathered to rank 0" % world,
+                       "weights": "synthetic calibrated seed 0 via load_weights", "bn": "folded (eval)",
+                       "l2": "inputs alternate between two %.0f MB frame batches and every step streams >1 GB of "
+                             "activations (> 126 MB L2)" % (B * 3 * RESO * RESO * 4 / 1e6),
+                       "detections_per_step": n_det / max(K, 1), "cuda_graph": bool(model.use_cuda_graph)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K,
+            "gpu_launches_per_step": launches_per_step,
+            "roofline": roofline, "roofline_nms": roofline_nms,
+            "forward_tflops": FRAME_GFLOP * world * B / (ms_total / K) if args.cfg == "yolov3" else None,
+            "latency_batch1": latency, "cpu_baseline": cpu, "layers": per_layer,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

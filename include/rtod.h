@@ -110,6 +110,14 @@ int rtod_plan_set_conv_weights(RtodPlan* plan, int layer, const float* weight, c
  * yolo layer. */
 int rtod_plan_forward(RtodPlan* plan, const float* x_nchw, float* pred, int train, void* stream);
 
+/* Measurement: same as rtod_plan_forward, but brackets every layer with CUDA events on `stream`,
+ * synchronises, and returns the device time of each layer's launch in layer_ms_host[0..n_layers)
+ * and of the decode launch in layer_ms_host[n_layers] (HOST arrays; layer_kind_host may be null:
+ * 0 = no kernel (alias/fused), 1 = tcgen05 conv, 2 = CUDA-core conv, 3 = stem conv, 4 = other). */
+int rtod_plan_forward_profile(RtodPlan* plan, const float* x_nchw, float* pred, int train, void* stream,
+                              float* layer_ms_host, int* layer_kind_host);
+double rtod_plan_layer_flops(const RtodPlan* plan, int layer); /* 2*M*N*K of one convolution  */
+
 /* Debug/validation: copy one layer's output to fp32 NCHW [batch, c, h, w].  Meaningful after a
  * forward of a plan created with RTOD_PLAN_KEEP_ALL (or for the last layer). */
 int rtod_plan_read_layer(RtodPlan* plan, int layer, float* out_nchw, void* stream);

@@ -498,8 +498,10 @@ extern "C" int rtod_plan_set_conv_weights(RtodPlan* p, int layer, const float* w
     return RTOD_OK;
 }
 
-extern "C" int rtod_plan_forward(RtodPlan* p, const float* x, float* pred, int train, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+// one forward; when `ev` is non-null it holds n_layers + 2 events: ev[0] before the first launch,
+// ev[i + 1] after layer i, ev[n + 1] after the decode launch
+static int run_forward(RtodPlan* p, const float* x, float* pred, int train, cudaStream_t stream,
+                       cudaEvent_t* ev) {
     if (!p || !p->bound) return fail(RTOD_ERR_STATE, "rtod_plan_forward: plan is not bound");
     if (!x) return fail(RTOD_ERR_BAD_ARG, "rtod_plan_forward: input is null");
     if (p->heads.count && !pred) return fail(RTOD_ERR_BAD_ARG, "rtod_plan_forward: pred is null");
@@ -508,9 +510,11 @@ extern "C" int rtod_plan_forward(RtodPlan* p, const float* x, float* pred, int t
         if (p->nodes[i].d.type == RTOD_LAYER_CONV && !p->nodes[i].weights_set)
             return fail(RTOD_ERR_STATE, "rtod_plan_forward: convolution %d has no weights", i);
     int rc;
+    if (ev) RTOD_CUDA_OK(cudaEventRecord(ev[0], stream));
     if (p->input_buf >= 0 && (rc = launch_nchw_to_nhwc(x, p->batch, act_of(*p, kInputLayer), stream))) return rc;
     for (int i = 0; i < n; ++i) {
         Node& nd = p->nodes[i];
+        if (ev && i > 0) RTOD_CUDA_OK(cudaEventRecord(ev[i], stream));
         if (nd.alias_of >= -1) continue;
         const RtodLayerDesc& d = nd.d;
         rc = RTOD_OK;
@@ -546,11 +550,51 @@ extern "C" int rtod_plan_forward(RtodPlan* p, const float* x, float* pred, int t
         }
         if (rc) return rc;
     }
+    if (ev) RTOD_CUDA_OK(cudaEventRecord(ev[n], stream));
     if (p->heads.count) {
         rc = launch_decode_heads(p->heads, p->batch, p->n_rows, p->n_attrs, train, pred, stream);
         if (rc) return rc;
     }
+    if (ev) RTOD_CUDA_OK(cudaEventRecord(ev[n + 1], stream));
     return RTOD_OK;
+}
+
+extern "C" int rtod_plan_forward(RtodPlan* p, const float* x, float* pred, int train, void* stream) {
+    return run_forward(p, x, pred, train, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int rtod_plan_forward_profile(RtodPlan* p, const float* x, float* pred, int train, void* stream_,
+                                         float* layer_ms_host, int* layer_kind_host) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!p || !layer_ms_host) return fail(RTOD_ERR_BAD_ARG, "rtod_plan_forward_profile: null argument");
+    const int n = (int)p->nodes.size();
+    std::vector<cudaEvent_t> ev(n + 2);
+    for (auto& e : ev) RTOD_CUDA_OK(cudaEventCreate(&e));
+    int rc = run_forward(p, x, pred, train, stream, ev.data());
+    if (!rc) {
+        cudaError_t err = cudaStreamSynchronize(stream);
+        if (err != cudaSuccess) rc = fail(RTOD_ERR_CUDA, "profile sync failed: %s", cudaGetErrorString(err));
+    }
+    for (int i = 0; i <= n && !rc; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+        layer_ms_host[i] = ms;                               // [n] = decode launch
+        if (layer_kind_host && i < n) {
+            const Node& nd = p->nodes[i];
+            // 0 = no kernel (alias / fused), 1 = tcgen05 conv, 2 = CUDA-core conv, 3 = stem, 4 = other
+            layer_kind_host[i] = nd.alias_of >= -1 ? 0
+                                 : nd.d.type != RTOD_LAYER_CONV ? (nd.d.type == RTOD_LAYER_ROUTE && !nd.copy_concat ? 0 : 4)
+                                 : nd.stem ? 3 : (nd.use_tc ? 1 : 2);
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+extern "C" double rtod_plan_layer_flops(const RtodPlan* p, int layer) {
+    if (!p || layer < 0 || layer >= (int)p->nodes.size() || p->nodes[layer].d.type != RTOD_LAYER_CONV) return 0.0;
+    const Node& nd = p->nodes[layer];
+    return 2.0 * (double)p->batch * nd.H * nd.W * nd.d.filters * nd.K;
 }
 
 extern "C" int rtod_plan_read_layer(RtodPlan* p, int layer, float* out_nchw, void* stream) {

@@ -1,0 +1,76 @@
+"""Streaming detection over host frames: pinned, asynchronous host->device copies on a side
+stream overlap the previous batch's forward + decode + NMS (BASELINE.json configs[4]; the
+reference's loop is detect.py:57-80 -- synchronous pageable ``.cuda()`` per image).
+
+    pipe = DetectionPipeline(model, num_class=80, confidence=0.5, nms_conf=0.4)
+    for det in pipe.run(host_batches):        # det: [D, 8] tensor on the host, or int 0
+        ...
+"""
+from __future__ import annotations
+
+import torch
+
+from .util import write_results
+
+
+class DetectionPipeline:
+    def __init__(self, model, num_class: int, confidence: float = 0.6, nms_conf: float = 0.4,
+                 device=None, depth: int = 2):
+        if not torch.cuda.is_available():
+            raise RuntimeError("DetectionPipeline needs a CUDA device; there is no CPU fallback")
+        self.model, self.num_class = model, int(num_class)
+        self.confidence, self.nms_conf = float(confidence), float(nms_conf)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.depth = max(2, int(depth))
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self._slots = []
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _slot(self, k, like):
+        while len(self._slots) <= k:
+            self._slots.append({"buf": None, "ready": torch.cuda.Event(), "free": torch.cuda.Event()})
+        s = self._slots[k]
+        if s["buf"] is None or s["buf"].shape != like.shape:
+            s["buf"] = torch.empty(like.shape, dtype=torch.float32, device=self.device)
+            s["free"].record(torch.cuda.current_stream(self.device))
+        return s
+
+    def _stage(self, k, host):
+        """enqueue the H2D copy of one host batch into ring slot k on the copy stream"""
+        s = self._slot(k % self.depth, host)
+        if not host.is_pinned():
+            host = host.pin_memory()
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(s["free"])           # previous user of the slot is done
+            s["buf"].copy_(host, non_blocking=True)
+            s["ready"].record(self.copy_stream)
+        self.h2d_bytes += host.numel() * host.element_size()
+        return s
+
+    def run(self, host_batches):
+        """host_batches: iterable of [B, 3, H, W] fp32 host tensors (pinned memory avoids a staging
+        copy).  Yields write_results() of every batch, on the host."""
+        it = iter(host_batches)
+        compute = torch.cuda.current_stream(self.device)
+        try:
+            pending = self._stage(0, next(it))
+        except StopIteration:
+            return
+        k = 0
+        while pending is not None:
+            nxt = None
+            try:
+                nxt = self._stage(k + 1, next(it))            # overlaps this batch's compute
+            except StopIteration:
+                pass
+            compute.wait_event(pending["ready"])
+            pred = self.model(pending["buf"])
+            det = write_results(pred, self.num_class, self.confidence, self.nms_conf)
+            pending["free"].record(compute)
+            if not isinstance(det, int):
+                det = det.cpu()
+                self.d2h_bytes += det.numel() * 4
+            self.d2h_bytes += 4                                # the detection count
+            yield det
+            pending, k = nxt, k + 1
