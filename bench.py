@@ -339,9 +339,9 @@ def run_b200(args):
     # ---- CPU baseline (rank 0, N=1 only; bounded sample) ------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, times = cpu_port_frames_per_s(cfg, stream, blocks, 4, 3, 4, 1)
+        fps, times = cpu_port_frames_per_s(cfg, stream, blocks, 32, 4, 4, 1)
         cpu = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "4 frames (one batch of 4) x 3 reps + 1 warm-up, oracle port, eval-mode BN, %.1f s"
+               "sample": "32 frames (batches of 4) x 4 reps + 1 warm-up, oracle port, eval-mode BN, %.1f s"
                          % sum(times)}
 
     if rank == 0:
