@@ -12,7 +12,9 @@
 //   * W (BN-folded, K-major bf16 [Cout_pad][K]) arrives through a 2-D tiled descriptor.
 //   * tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN<=256, K=16) accumulates in TMEM; one
 //     elected thread issues, tcgen05.commit releases shared-memory stages back to the TMA
-//     producer through mbarriers and finally publishes the accumulator to the epilogue.
+//     producer through mbarriers and publishes each finished accumulator to the epilogue.
+//   * persistent CTAs (one per SM) loop over output tiles; the accumulator is double-buffered in
+//     TMEM (2 x BN columns) so the epilogue of one tile overlaps the MMAs of the next.
 //   * four epilogue warps read TMEM with tcgen05.ld (32 lanes x 32 columns), add the folded
 //     bias, apply leaky 0.1, add the shortcut operand, and store NHWC bf16 (or the fp32 logits
 //     of a detection head) with 16-byte vector stores -- possibly into a channel slice of a
@@ -28,7 +30,9 @@ namespace rtod {
 namespace {
 
 constexpr int kThreads = 192;
+constexpr int kEpilogueWarps = 4;
 constexpr int kBM = 128;
+constexpr uint32_t kSmemBudget = 200 * 1024;   // operand ring per CTA (one CTA per SM)
 constexpr unsigned long long kWaitTimeoutNs = 2000000000ull;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -39,6 +43,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
                  "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
@@ -143,7 +150,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t row_bytes)
 }
 
 // =============================================================================================
-__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+// Persistent: one CTA per SM walks output tiles (m fastest, so concurrently running CTAs share the
+// weight tile in L2).  The accumulator is double-buffered in TMEM, so the epilogue of tile i runs
+// while the tensor core already works on tile i+1, and the TMA producer runs ahead across tile
+// boundaries as far as the shared-memory ring allows.
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -154,11 +165,11 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     const uint32_t stage_bytes = a_bytes + b_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* empty_bar = full_bar + p.stages;
-    uint64_t* accum_bar = empty_bar + p.stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* acc_full = empty_bar + p.stages;          // [2] MMA -> epilogue
+    uint64_t* acc_empty = acc_full + 2;                 // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int num_kb = p.ks * p.ks * p.cchunks;
-    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * p.BN;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.tmA);
@@ -169,7 +180,10 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(accum_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], kEpilogueWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -181,28 +195,32 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            int ow = 0, oh = 0, on = 0;
-            if (p.ks > 1) {                      // first output pixel of the tile -> input coords
-                ow = (m0 % p.Wo) * p.stride - p.pad;
-                oh = ((m0 / p.Wo) % p.Ho) * p.stride - p.pad;
-                on = m0 / (p.Wo * p.Ho);
-            }
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag)) break;
-                uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
-                mbar_expect_tx(&full_bar[stage], stage_bytes);
-                const int tap = kb / p.cchunks, c0 = (kb - tap * p.cchunks) * p.BK;
-                if (p.ks > 1)
-                    tma_load_im2col_4d(a_dst, &p.tmA, &full_bar[stage], c0, ow, oh, on,
-                                       (uint16_t)(tap % p.ks), (uint16_t)(tap / p.ks));
-                else
-                    tma_load_2d(a_dst, &p.tmA, &full_bar[stage], c0, m0);
-                tma_load_2d(a_dst + a_bytes, &p.tmB, &full_bar[stage], kb * p.BK, n0);
-                if (++stage == p.stages) {
-                    stage = 0;
-                    phase ^= 1u;
+            bool ok = true;
+            for (int tile = blockIdx.x; ok && tile < p.total_tiles; tile += gridDim.x) {
+                const int m0 = (tile % p.m_tiles) * kBM, n0 = (tile / p.m_tiles) * p.BN;
+                int ow = 0, oh = 0, on = 0;
+                if (p.ks > 1) {                  // first output pixel of the tile -> input coords
+                    ow = (m0 % p.Wo) * p.stride - p.pad;
+                    oh = ((m0 / p.Wo) % p.Ho) * p.stride - p.pad;
+                    on = m0 / (p.Wo * p.Ho);
+                }
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag)) { ok = false; break; }
+                    uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
+                    mbar_expect_tx(&full_bar[stage], stage_bytes);
+                    const int tap = kb / p.cchunks, c0 = (kb - tap * p.cchunks) * p.BK;
+                    if (p.ks > 1)
+                        tma_load_im2col_4d(a_dst, &p.tmA, &full_bar[stage], c0, ow, oh, on,
+                                           (uint16_t)(tap % p.ks), (uint16_t)(tap / p.ks));
+                    else
+                        tma_load_2d(a_dst, &p.tmA, &full_bar[stage], c0, m0);
+                    tma_load_2d(a_dst + a_bytes, &p.tmB, &full_bar[stage], kb * p.BK, n0);
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
                 }
             }
         }
@@ -211,73 +229,93 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                if (!mbar_wait(&full_bar[stage], phase, p.err_flag)) break;
+            bool ok = true;
+            int local = 0;
+            for (int tile = blockIdx.x; ok && tile < p.total_tiles; tile += gridDim.x, ++local) {
+                const int buf = local & 1;
+                const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
+                if (!mbar_wait(&acc_empty[buf], acc_phase ^ 1u, p.err_flag)) break;   // epilogue drained it
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint32_t b_addr = a_addr + a_bytes;
-                for (int k = 0; k < p.BK / 16; ++k)
-                    umma_bf16(tmem_base, smem_desc(a_addr + k * 32, row_bytes),
-                              smem_desc(b_addr + k * 32, row_bytes), p.idesc, (uint32_t)(kb | k));
-                umma_commit(&empty_bar[stage]);              // frees the stage when the MMAs retire
-                if (++stage == p.stages) {
-                    stage = 0;
-                    phase ^= 1u;
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (!mbar_wait(&full_bar[stage], phase, p.err_flag)) { ok = false; break; }
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t b_addr = a_addr + a_bytes;
+                    for (int k = 0; k < p.BK / 16; ++k)
+                        umma_bf16(tmem_acc, smem_desc(a_addr + k * 32, row_bytes),
+                                  smem_desc(b_addr + k * 32, row_bytes), p.idesc, (uint32_t)(kb | k));
+                    umma_commit(&empty_bar[stage]);          // frees the stage when the MMAs retire
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
                 }
+                umma_commit(&acc_full[buf]);                 // accumulator of this tile complete
             }
-            umma_commit(accum_bar);                          // accumulator complete
         }
     } else {
         // ================= epilogue: TMEM -> registers -> global =================
         const int quarter = warp & 3;                        // TMEM lanes [32*quarter, +32)
-        const bool ok = mbar_wait(accum_bar, 0u, p.err_flag);
-        tc_fence_after();
-        const long long m = (long long)m0 + quarter * 32 + lane;
-        const bool row_ok = ok && m < p.M;
-        for (int c = 0; c < p.BN / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
-            if (!row_ok) continue;
-            const int nc = n0 + c * 32;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+            const int buf = local & 1;
+            const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
+            const int m0 = (tile % p.m_tiles) * kBM, n0 = (tile / p.m_tiles) * p.BN;
+            if (!mbar_wait(&acc_full[buf], acc_phase, p.err_flag)) break;
+            tc_fence_after();
+            const long long m = (long long)m0 + quarter * 32 + lane;
+            const bool row_ok = m < p.M;
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.BN) + ((uint32_t)(quarter * 32) << 16);
+            for (int c = 0; c < p.BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_acc + (uint32_t)(c * 32), v);
+                if (!row_ok) continue;
+                const int nc = n0 + c * 32;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int n = nc + g * 8;
-                if (n >= p.store_limit) break;
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                float f[8];
-                f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
-                f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
-                f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
-                f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
-                f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
-                f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
-                f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
-                f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
-                if (p.leaky) {
+                for (int g = 0; g < 4; ++g) {
+                    const int n = nc + g * 8;
+                    if (n >= p.store_limit) break;
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                    float f[8];
+                    f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
+                    f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+                    f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
+                    f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+                    f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
+                    f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+                    f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
+                    f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+                    if (p.leaky) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] = leaky01(f[j]);
-                }
-                if (p.res) {
-                    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p.res + m * p.res_pitch + n));
-                    f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
-                    f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
-                    f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
-                    f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
-                }
-                if (p.out_fp32) {
-                    float* dst = reinterpret_cast<float*>(p.out) + m * p.out_pitch + n;
-                    *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
-                    *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                } else {
-                    uint4 o;
-                    o.x = pack_bf16x2(f[0], f[1]);
-                    o.y = pack_bf16x2(f[2], f[3]);
-                    o.z = pack_bf16x2(f[4], f[5]);
-                    o.w = pack_bf16x2(f[6], f[7]);
-                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.out_pitch + n) = o;
+                        for (int j = 0; j < 8; ++j) f[j] = leaky01(f[j]);
+                    }
+                    if (p.res) {
+                        const uint4 r = __ldg(reinterpret_cast<const uint4*>(p.res + m * p.res_pitch + n));
+                        f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
+                        f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+                        f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
+                        f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+                    }
+                    if (p.out_fp32) {
+                        float* dst = reinterpret_cast<float*>(p.out) + m * p.out_pitch + n;
+                        *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+                        *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                    } else {
+                        uint4 o;
+                        o.x = pack_bf16x2(f[0], f[1]);
+                        o.y = pack_bf16x2(f[2], f[3]);
+                        o.z = pack_bf16x2(f[4], f[5]);
+                        o.w = pack_bf16x2(f[6], f[7]);
+                        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.out_pitch + n) = o;
+                    }
                 }
             }
+            // this warp has read its 32 lanes of the buffer: hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
         tc_fence_before();
     }
@@ -340,7 +378,8 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     }
     ConvTcParams& p = launch->p;
     const int BK = pick_bk(a.Cin);
-    int BN = a.Cout_pad < 128 ? a.Cout_pad : 128;
+    int BN = a.Cout_pad < 256 ? a.Cout_pad : 256;       // widest tile the single-CTA MMA supports
+    if (a.Cout_pad % BN != 0) BN = 128;
     if (a.Cout_pad % BN != 0 || BN % 32 != 0)
         return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: Cout_pad %d not tileable", a.Cout_pad);
     const long long M = (long long)a.B * a.out.H * a.out.W;
@@ -365,17 +404,19 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     p.stride = a.stride;
     p.pad = a.pad;
     int cols = 32;
-    while (cols < BN) cols <<= 1;
+    while (cols < 2 * BN) cols <<= 1;                    // two accumulator buffers
     p.tmem_cols = cols;
     // c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major both, N>>3 at 17, M>>4 at 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
     const uint32_t stage_bytes = (uint32_t)(kBM + BN) * BK * 2;
-    int stages = (int)(98304u / stage_bytes);
+    int stages = (int)(kSmemBudget / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     p.stages = stages;
-    launch->smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
-    launch->grid = dim3((unsigned)((M + kBM - 1) / kBM), (unsigned)(a.Cout_pad / BN), 1);
+    p.m_tiles = (int)((M + kBM - 1) / kBM);
+    p.total_tiles = p.m_tiles * (a.Cout_pad / BN);
+    launch->smem_bytes = stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+    launch->grid = dim3((unsigned)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs), 1, 1);
 
     // ---- A ----
     const cuuint32_t estr1[4] = {1, 1, 1, 1};
@@ -423,7 +464,7 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
                         a.Cout_pad, (int)r);
     }
     RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)launch->smem_bytes > 200 * 1024 ? (int)launch->smem_bytes : 200 * 1024));
+                                      227 * 1024));
     return RTOD_OK;
 }
 

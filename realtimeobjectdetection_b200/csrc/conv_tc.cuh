@@ -20,7 +20,8 @@ struct alignas(64) ConvTcParams {
     int ks, cchunks;            // kernel size, Cin / BK
     int BK, BN, stages;         // K tile (16/32/64 -> 32B/64B/128B swizzle), N tile, pipeline depth
     int Ho, Wo, stride, pad;    // im2col traversal
-    int tmem_cols;
+    int tmem_cols;              // 2 * BN rounded up to a power of two
+    int m_tiles, total_tiles;   // tile = m_tile + m_tiles * n_tile
     uint32_t idesc;             // tcgen05 instruction descriptor (bf16 x bf16 -> fp32, M=128, N=BN)
 };
 

@@ -160,6 +160,49 @@ def stage_timing():
     print("write_results [256,10647,85] 1%%: %.3f ms -> %.1f GB/s, dets %d" % (ms, pred.numel() * 4 / ms / 1e6, len(det)))
 
 
+def stage_layers():
+    """per-layer device time (CUDA events around every launch) for B in argv[2:] (default 64 1)"""
+    import ctypes
+    lib = _lib.load()
+    cfg, blocks, stream, state = make_network("yolov3", 3, "calibrated")
+    batches = [int(v) for v in sys.argv[2:]] or [64, 1]
+    for batch in batches:
+        model = Darknet(cfg, True)
+        model.load_state_dict({**model.state_dict(), **state})
+        model.eval()
+        model.use_cuda_graph = False
+        x = torch.rand(batch, 3, 416, 416, device="cuda")
+        model(x)
+        plan = next(iter(model._plans.values()))
+        n = len(blocks) - 1
+        ms = (ctypes.c_float * (n + 1))()
+        kind = (ctypes.c_int * n)()
+        pred = torch.empty(batch, plan.n_rows, plan.n_attrs, device="cuda")
+        acc = [0.0] * (n + 1)
+        reps = 5
+        for r in range(reps + 1):
+            _lib.check(lib.rtod_plan_forward_profile(plan.handle, x.data_ptr(), pred.data_ptr(), 0,
+                                                     torch.cuda.current_stream().cuda_stream, ms, kind))
+            if r:
+                for i in range(n + 1):
+                    acc[i] += ms[i] / reps
+        model.check_device()
+        tot = sum(acc)
+        print("B=%d total %.3f ms" % (batch, tot))
+        for i in range(n):
+            if not kind[i]:
+                continue
+            blk = blocks[i + 1]
+            fl = lib.rtod_plan_layer_flops(plan.handle, i)
+            c, h, w = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+            lib.rtod_plan_layer_shape(plan.handle, i, ctypes.byref(c), ctypes.byref(h), ctypes.byref(w))
+            desc = "%s k%s s%s" % (blk["type"][:4], blk.get("size", "-"), blk.get("stride", "-"))
+            print("  L%3d kind %d %-14s -> %4dx%3dx%3d  %8.1f us  %7.1f TF/s  %5.1f%%" %
+                  (i, kind[i], desc, c.value, h.value, w.value, acc[i] * 1e3, fl / max(acc[i], 1e-9) / 1e9,
+                   100 * acc[i] / tot))
+        print("  decode %8.1f us" % (acc[n] * 1e3))
+
+
 if __name__ == "__main__":
     stage = sys.argv[1]
     torch.backends.cudnn.allow_tf32 = False
