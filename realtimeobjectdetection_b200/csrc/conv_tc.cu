@@ -16,9 +16,11 @@
 //   * persistent CTAs (one per SM) loop over output tiles; the accumulator is double-buffered in
 //     TMEM (2 x BN columns) so the epilogue of one tile overlaps the MMAs of the next.
 //   * four epilogue warps read TMEM with tcgen05.ld (32 lanes x 32 columns), add the folded
-//     bias, apply leaky 0.1, add the shortcut operand, and store NHWC bf16 (or the fp32 logits
-//     of a detection head) with 16-byte vector stores -- possibly into a channel slice of a
-//     route/concat buffer (src/darknet.py:285-288 becomes zero-copy).
+//     bias, apply leaky 0.1, add the shortcut operand (itself TMA-loaded into swizzled smem two
+//     chunks ahead), write bf16 (or the fp32 logits of a detection head) into a swizzled
+//     staging tile and hand it to a TMA store -- possibly into a channel slice of a
+//     route/concat buffer (src/darknet.py:285-288 becomes zero-copy); rows beyond M and channels
+//     beyond Cout are clipped by the descriptor.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue
 // (warp 2 also owns the TMEM allocation).  Every mbarrier wait is bounded: on a time-out the
@@ -32,7 +34,8 @@ namespace {
 constexpr int kThreads = 192;
 constexpr int kEpilogueWarps = 4;
 constexpr int kBM = 128;
-constexpr uint32_t kSmemBudget = 200 * 1024;   // operand ring per CTA (one CTA per SM)
+constexpr uint32_t kStageTile = 16384;         // epilogue staging tile: 128 rows x 128 B
+constexpr uint32_t kSmemLimit = 225 * 1024;    // dynamic shared memory per CTA (one CTA per SM)
 constexpr unsigned long long kWaitTimeoutNs = 2000000000ull;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -61,6 +64,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // bounded wait: false after a time-out or once another CTA has raised the failure flag
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
     if (mbar_try_wait(bar, parity)) return true;
+    if (*(volatile int*)err_flag != 0) return false;
     const unsigned long long t0 = global_timer_ns();
     unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -91,6 +95,20 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap*
         " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
         : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() {      // all but the newest group have read their smem
+    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier(int id) {      // the 128 epilogue threads only
+    asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -126,6 +144,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                      smem_u32(bar))
                  : "memory");
+}
+// byte offset of 16-byte chunk j of row r inside a TMA-swizzled staging tile whose rows are
+// row_bytes (64 or 128) wide: the chunk index is XORed with address bits [7, ...)
+__device__ __forceinline__ uint32_t staged_offset(int r, int j, uint32_t row_bytes) {
+    const uint32_t sw = row_bytes == 128 ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
+    return (uint32_t)r * row_bytes + (((uint32_t)j ^ sw) << 4);
 }
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -163,17 +187,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t row_bytes = (uint32_t)p.BK * 2u;
     const uint32_t a_bytes = kBM * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
     const uint32_t stage_bytes = a_bytes + b_bytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint8_t* out_stage = smem + (size_t)p.stages * stage_bytes;          // [2][kStageTile] epilogue -> TMA store
+    uint8_t* res_stage = out_stage + 2 * kStageTile;                     // [2][kStageTile] shortcut operand
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(res_stage + (p.has_res ? 2 * kStageTile : 0));
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* acc_full = empty_bar + p.stages;          // [2] MMA -> epilogue
     uint64_t* acc_empty = acc_full + 2;                 // [2] epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* res_full = acc_empty + 2;                 // [2] TMA (shortcut operand) -> epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
 
     const int num_kb = p.ks * p.ks * p.cchunks;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.tmA);
         prefetch_tmap(&p.tmB);
+        prefetch_tmap(&p.tmOut);
+        if (p.has_res) prefetch_tmap(&p.tmRes);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -183,6 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
             mbar_init(&acc_empty[b], kEpilogueWarps);
+            mbar_init(&res_full[b], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -255,68 +285,108 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
         }
     } else {
-        // ================= epilogue: TMEM -> registers -> global =================
+        // ================= epilogue: TMEM -> registers -> swizzled smem -> TMA store ============
+        // A chunk is 128 rows x one staging row (128 B: 64 bf16 or 32 fp32 channels; 64 B when the
+        // tile is only 32 bf16 channels wide).  Chunks are numbered continuously across tiles (g):
+        // staging buffer g & 1, so that the TMA store of chunk g and the TMA load of the shortcut
+        // operand of chunk g + 2 overlap the arithmetic of chunk g + 1.
         const int quarter = warp & 3;                        // TMEM lanes [32*quarter, +32)
+        const int row = quarter * 32 + lane;                 // row of the tile this thread owns
+        const bool leader = warp == 2 && lane == 0;
+        const int ecols = p.ecols;
+        const uint32_t erow = (uint32_t)ecols * (p.out_fp32 ? 4u : 2u);
+        const int n_chunks = p.BN / ecols;
+        auto issue_res = [&](uint32_t g) {                   // leader only
+            const int tl = (int)(g / (uint32_t)n_chunks), c = (int)(g - (uint32_t)tl * n_chunks);
+            const int t = blockIdx.x + tl * gridDim.x;
+            if (t >= p.total_tiles) return;
+            mbar_expect_tx(&res_full[g & 1], kBM * erow);
+            tma_load_2d(res_stage + (g & 1) * kStageTile, &p.tmRes, &res_full[g & 1],
+                        (t / p.m_tiles) * p.BN + c * ecols, (t % p.m_tiles) * kBM);
+        };
+        if (p.has_res && leader) {
+            issue_res(0);
+            issue_res(1);
+        }
+        // NOTE: no early exit in this role: the named barriers below must be reached by all 128
+        // threads the same number of times.  After a time-out (*err_flag != 0) every wait returns
+        // at once, so the loop drains quickly and the host sees the flag.
+        uint32_t g = 0;
         int local = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
             const int buf = local & 1;
             const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
             const int m0 = (tile % p.m_tiles) * kBM, n0 = (tile / p.m_tiles) * p.BN;
-            if (!mbar_wait(&acc_full[buf], acc_phase, p.err_flag)) break;
+            mbar_wait(&acc_full[buf], acc_phase, p.err_flag);
             tc_fence_after();
-            const long long m = (long long)m0 + quarter * 32 + lane;
-            const bool row_ok = m < p.M;
             const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.BN) + ((uint32_t)(quarter * 32) << 16);
-            for (int c = 0; c < p.BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_acc + (uint32_t)(c * 32), v);
-                if (!row_ok) continue;
-                const int nc = n0 + c * 32;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int n = nc + g * 8;
-                    if (n >= p.store_limit) break;
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                    float f[8];
-                    f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
-                    f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
-                    f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
-                    f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
-                    f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
-                    f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
-                    f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
-                    f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
-                    if (p.leaky) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] = leaky01(f[j]);
+            for (int c = 0; c < n_chunks; ++c, ++g) {
+                uint8_t* ostage = out_stage + (g & 1) * kStageTile;
+                const uint8_t* rstage = res_stage + (g & 1) * kStageTile;
+                if (leader) bulk_wait_read_1();              // the store that last used ostage has drained
+                epi_barrier(1);
+                if (p.has_res) mbar_wait(&res_full[g & 1], (g >> 1) & 1u, p.err_flag);
+                const int halves = p.out_fp32 ? 1 : (ecols + 31) / 32;      // 32 accumulator columns each
+                for (int h = 0; h < halves; ++h) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_acc + (uint32_t)(c * ecols + h * 32), v);
+                    if (c == n_chunks - 1 && h == halves - 1) {
+                        // last TMEM read of this tile: hand the accumulator back to the MMA issuer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[buf]);
                     }
-                    if (p.res) {
-                        const uint4 r = __ldg(reinterpret_cast<const uint4*>(p.res + m * p.res_pitch + n));
-                        f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
-                        f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
-                        f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
-                        f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
-                    }
-                    if (p.out_fp32) {
-                        float* dst = reinterpret_cast<float*>(p.out) + m * p.out_pitch + n;
-                        *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
-                        *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                    } else {
-                        uint4 o;
-                        o.x = pack_bf16x2(f[0], f[1]);
-                        o.y = pack_bf16x2(f[2], f[3]);
-                        o.z = pack_bf16x2(f[4], f[5]);
-                        o.w = pack_bf16x2(f[6], f[7]);
-                        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.out_pitch + n) = o;
+                    const int nbase = n0 + c * ecols + h * 32;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + q * 8));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + q * 8 + 4));
+                        float f[8];
+                        f[0] = __uint_as_float(v[q * 8 + 0]) + b0.x;
+                        f[1] = __uint_as_float(v[q * 8 + 1]) + b0.y;
+                        f[2] = __uint_as_float(v[q * 8 + 2]) + b0.z;
+                        f[3] = __uint_as_float(v[q * 8 + 3]) + b0.w;
+                        f[4] = __uint_as_float(v[q * 8 + 4]) + b1.x;
+                        f[5] = __uint_as_float(v[q * 8 + 5]) + b1.y;
+                        f[6] = __uint_as_float(v[q * 8 + 6]) + b1.z;
+                        f[7] = __uint_as_float(v[q * 8 + 7]) + b1.w;
+                        if (p.leaky) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = leaky01(f[j]);
+                        }
+                        if (p.out_fp32) {                    // 8 fp32 = two 16-byte chunks
+                            *reinterpret_cast<float4*>(ostage + staged_offset(row, q * 2, erow)) =
+                                make_float4(f[0], f[1], f[2], f[3]);
+                            *reinterpret_cast<float4*>(ostage + staged_offset(row, q * 2 + 1, erow)) =
+                                make_float4(f[4], f[5], f[6], f[7]);
+                        } else {
+                            const uint32_t off = staged_offset(row, h * 4 + q, erow);
+                            if (p.has_res) {
+                                const uint4 r = *reinterpret_cast<const uint4*>(rstage + off);
+                                f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
+                                f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+                                f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
+                                f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+                            }
+                            uint4 o;
+                            o.x = pack_bf16x2(f[0], f[1]);
+                            o.y = pack_bf16x2(f[2], f[3]);
+                            o.z = pack_bf16x2(f[4], f[5]);
+                            o.w = pack_bf16x2(f[6], f[7]);
+                            *reinterpret_cast<uint4*>(ostage + off) = o;
+                        }
                     }
                 }
+                fence_async_smem();                          // generic-proxy writes -> visible to the TMA
+                epi_barrier(2);
+                if (leader) {
+                    tma_store_2d(&p.tmOut, ostage, n0 + c * ecols, m0);   // rows >= M / cols >= Cout are clipped
+                    bulk_commit();
+                    if (p.has_res) issue_res(g + 2);
+                }
             }
-            // this warp has read its 32 lanes of the buffer: hand it back to the MMA issuer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
+        if (leader) bulk_wait_all();
         tc_fence_before();
     }
 
@@ -383,17 +453,11 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     if (a.Cout_pad % BN != 0 || BN % 32 != 0)
         return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: Cout_pad %d not tileable", a.Cout_pad);
     const long long M = (long long)a.B * a.out.H * a.out.W;
-    p.out = a.out.ptr;
     p.bias = a.bias;
-    p.res = a.res;
     p.err_flag = err_flag;
-    p.out_pitch = a.out.pitch;
     p.out_fp32 = a.out.fp32;
-    p.res_pitch = a.res_pitch;
     p.M = (int)M;
     p.Cout = a.Cout;
-    p.store_limit = a.out.fp32 ? (((a.Cout + 7) / 8 * 8) < a.out.pitch ? ((a.Cout + 7) / 8 * 8) : a.out.pitch)
-                               : a.Cout;
     p.leaky = a.leaky;
     p.ks = a.ks;
     p.cchunks = a.Cin / BK;
@@ -409,13 +473,16 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     // c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major both, N>>3 at 17, M>>4 at 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
     const uint32_t stage_bytes = (uint32_t)(kBM + BN) * BK * 2;
-    int stages = (int)(kSmemBudget / stage_bytes);
+    p.has_res = a.res != nullptr;
+    p.ecols = a.out.fp32 ? 32 : (BN < 64 ? BN : 64);
+    const uint32_t fixed = 1024 /*alignment slack*/ + 2 * kStageTile + (p.has_res ? 2 * kStageTile : 0) + 512;
+    int stages = (int)((kSmemLimit - fixed) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     p.stages = stages;
     p.m_tiles = (int)((M + kBM - 1) / kBM);
     p.total_tiles = p.m_tiles * (a.Cout_pad / BN);
-    launch->smem_bytes = stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+    launch->smem_bytes = stages * stage_bytes + fixed;
     launch->grid = dim3((unsigned)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs), 1, 1);
 
     // ---- A ----
@@ -462,6 +529,28 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
         if (r != CUDA_SUCCESS)
             return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (weights, K=%d Cout_pad=%d) failed: %d", a.K,
                         a.Cout_pad, (int)r);
+    }
+    // ---- epilogue: output tile store, shortcut operand load (same 128-row x 128-byte box) ----
+    {
+        const size_t esz = a.out.fp32 ? 4 : 2;
+        const CUtensorMapDataType dt = a.out.fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        const CUtensorMapSwizzle sw = p.ecols * esz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+        const cuuint64_t dims[2] = {(cuuint64_t)a.Cout, (cuuint64_t)M};
+        const cuuint64_t strides[1] = {(cuuint64_t)a.out.pitch * esz};
+        const cuuint32_t box[2] = {(cuuint32_t)p.ecols, (cuuint32_t)kBM};
+        r = encode_tiled(&p.tmOut, dt, 2, a.out.ptr, dims, strides, box, estr1, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+            return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (output, Cout=%d pitch=%d) failed: %d", a.Cout,
+                        a.out.pitch, (int)r);
+        if (p.has_res) {
+            const cuuint64_t rstrides[1] = {(cuuint64_t)a.res_pitch * 2};
+            r = encode_tiled(&p.tmRes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.res), dims,
+                             rstrides, box, estr1, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS)
+                return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (shortcut operand) failed: %d", (int)r);
+        }
     }
     RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       227 * 1024));

@@ -10,12 +10,13 @@ namespace rtod {
 struct alignas(64) ConvTcParams {
     CUtensorMap tmA;            // activations: 2-D tiled {C, M} (1x1) or 4-D im2col {C, W, H, N} (3x3)
     CUtensorMap tmB;            // weights: 2-D tiled {K, Cout_pad}
-    void* out;                  // NHWC bf16 (or fp32 head logits), pixel pitch out_pitch elements
+    CUtensorMap tmOut;          // output: 2-D tiled {Cout, M}, NHWC bf16 (fp32 for head logits)
+    CUtensorMap tmRes;          // shortcut operand: 2-D tiled {Cout, M} bf16 (valid iff has_res)
     const float* bias;          // [Cout_pad]
-    const __nv_bfloat16* res;   // shortcut operand or null
     int* err_flag;              // device-side failure flag (pipeline time-out)
-    int out_pitch, out_fp32, res_pitch;
-    int M, Cout, store_limit;   // output pixels, real channels, channels actually stored
+    int out_fp32, has_res;
+    int ecols;                  // channels per epilogue chunk (one staging row: 64 bf16 / 32 fp32)
+    int M, Cout;                // output pixels, real channels
     int leaky;
     int ks, cchunks;            // kernel size, Cin / BK
     int BK, BN, stages;         // K tile (16/32/64 -> 32B/64B/128B swizzle), N tile, pipeline depth
