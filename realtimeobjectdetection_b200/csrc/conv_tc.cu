@@ -27,6 +27,8 @@
 // kernel raises *err_flag and drains instead of hanging the GPU.
 #include "conv_tc.cuh"
 
+#include <cstdlib>
+
 namespace rtod {
 
 namespace {
@@ -36,6 +38,7 @@ constexpr int kEpilogueWarps = 4;
 constexpr int kBM = 128;
 constexpr uint32_t kStageTile = 16384;         // epilogue staging tile: 128 rows x 128 B
 constexpr uint32_t kSmemLimit = 225 * 1024;    // dynamic shared memory per CTA (one CTA per SM)
+constexpr uint32_t kResidentLimit = 100 * 1024; // largest weight matrix kept resident in shared memory
 constexpr unsigned long long kWaitTimeoutNs = 2000000000ull;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -186,15 +189,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t row_bytes = (uint32_t)p.BK * 2u;
     const uint32_t a_bytes = kBM * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
-    const uint32_t stage_bytes = a_bytes + b_bytes;
-    uint8_t* out_stage = smem + (size_t)p.stages * stage_bytes;          // [2][kStageTile] epilogue -> TMA store
+    const uint32_t stage_bytes = a_bytes + (p.b_resident ? 0u : b_bytes);
+    // ring stages hold {A, B} tiles, or A tiles only when the whole weight matrix is resident
+    uint8_t* b_resident = smem + (size_t)p.stages * stage_bytes;         // [num_kb][BN x BK] iff p.b_resident
+    uint8_t* out_stage = b_resident + (p.b_resident ? (size_t)p.ks * p.ks * p.cchunks * b_bytes : 0);
     uint8_t* res_stage = out_stage + 2 * kStageTile;                     // [2][kStageTile] shortcut operand
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(res_stage + (p.has_res ? 2 * kStageTile : 0));
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* acc_full = empty_bar + p.stages;          // [2] MMA -> epilogue
     uint64_t* acc_empty = acc_full + 2;                 // [2] epilogue -> MMA
     uint64_t* res_full = acc_empty + 2;                 // [2] TMA (shortcut operand) -> epilogue
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+    uint64_t* wres_bar = res_full + 2;                  // [1] resident weights have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
 
     const int num_kb = p.ks * p.ks * p.cchunks;
 
@@ -214,6 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             mbar_init(&acc_empty[b], kEpilogueWarps);
             mbar_init(&res_full[b], 1);
         }
+        mbar_init(wres_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -228,6 +235,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
+            if (p.b_resident) {                  // single N tile: the whole [BN x K] weight matrix, once
+                mbar_expect_tx(wres_bar, (uint32_t)num_kb * b_bytes);
+                for (int kb = 0; kb < num_kb; ++kb)
+                    tma_load_2d(b_resident + (size_t)kb * b_bytes, &p.tmB, wres_bar, kb * p.BK, 0);
+            }
             for (int tile = blockIdx.x; ok && tile < p.total_tiles; tile += gridDim.x) {
                 const int m0 = (tile % p.m_tiles) * kBM, n0 = (tile / p.m_tiles) * p.BN;
                 int ow = 0, oh = 0, on = 0;
@@ -246,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                            (uint16_t)(tap % p.ks), (uint16_t)(tap / p.ks));
                     else
                         tma_load_2d(a_dst, &p.tmA, &full_bar[stage], c0, m0);
-                    tma_load_2d(a_dst + a_bytes, &p.tmB, &full_bar[stage], kb * p.BK, n0);
+                    if (!p.b_resident) tma_load_2d(a_dst + a_bytes, &p.tmB, &full_bar[stage], kb * p.BK, n0);
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1u;
@@ -261,6 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             uint32_t phase = 0;
             bool ok = true;
             int local = 0;
+            if (p.b_resident) ok = mbar_wait(wres_bar, 0u, p.err_flag);
             for (int tile = blockIdx.x; ok && tile < p.total_tiles; tile += gridDim.x, ++local) {
                 const int buf = local & 1;
                 const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
@@ -271,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     if (!mbar_wait(&full_bar[stage], phase, p.err_flag)) { ok = false; break; }
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t b_addr = a_addr + a_bytes;
+                    const uint32_t b_addr = p.b_resident ? smem_u32(b_resident + (size_t)kb * b_bytes) : a_addr + a_bytes;
                     for (int k = 0; k < p.BK / 16; ++k)
                         umma_bf16(tmem_acc, smem_desc(a_addr + k * 32, row_bytes),
                                   smem_desc(b_addr + k * 32, row_bytes), p.idesc, (uint32_t)(kb | k));
@@ -475,14 +488,22 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     const uint32_t stage_bytes = (uint32_t)(kBM + BN) * BK * 2;
     p.has_res = a.res != nullptr;
     p.ecols = a.out.fp32 ? 32 : (BN < 64 ? BN : 64);
-    const uint32_t fixed = 1024 /*alignment slack*/ + 2 * kStageTile + (p.has_res ? 2 * kStageTile : 0) + 512;
-    int stages = (int)((kSmemLimit - fixed) / stage_bytes);
+    uint32_t fixed = 1024 /*alignment slack*/ + 2 * kStageTile + (p.has_res ? 2 * kStageTile : 0) + 512;
+    // small layers: keep the whole weight matrix in shared memory and stream activations only
+    const uint32_t w_bytes = (uint32_t)BN * a.K * 2;
+    p.b_resident = (a.Cout_pad == BN && w_bytes <= kResidentLimit && getenv("RTOD_TC_NO_RESIDENT") == nullptr) ? 1 : 0;
+    uint32_t stage_bytes_eff = stage_bytes;
+    if (p.b_resident) {
+        fixed += w_bytes;
+        stage_bytes_eff = (uint32_t)kBM * BK * 2;
+    }
+    int stages = (int)((kSmemLimit - fixed) / stage_bytes_eff);
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     p.stages = stages;
     p.m_tiles = (int)((M + kBM - 1) / kBM);
     p.total_tiles = p.m_tiles * (a.Cout_pad / BN);
-    launch->smem_bytes = stages * stage_bytes + fixed;
+    launch->smem_bytes = stages * stage_bytes_eff + fixed;
     launch->grid = dim3((unsigned)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs), 1, 1);
 
     // ---- A ----

@@ -56,23 +56,38 @@ yolo_decode_nchw_kernel(const float* __restrict__ head, int G, int A, int L, flo
     }
 }
 
+// One warp per (image, head, cell): the A*(5+C) logits of a cell are contiguous in the NHWC head
+// buffer and its A prediction rows are contiguous in the output, so both sides are coalesced and
+// the index arithmetic is done once per warp instead of once per element.
 __global__ void __launch_bounds__(256)
-yolo_decode_heads_kernel(DecodeHeads heads, int B, int N, int L, int train, float* __restrict__ pred) {
-    const long long total = (long long)B * N * L;
-    for (long long e = blockIdx.x * 256ll + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
-        const int attr = (int)(e % L);
-        const long long br = e / L;
-        const int row = (int)(br % N), b = (int)(br / N);
+yolo_decode_heads_kernel(DecodeHeads heads, int B, int N, int L, int train, int cells_per_image,
+                         float* __restrict__ pred) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long total = (long long)B * cells_per_image;
+    for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += warps) {
+        const int b = (int)(w / cells_per_image);
+        int cell = (int)(w - (long long)b * cells_per_image);
         int h = 0;
 #pragma unroll
-        for (int k = 1; k < kMaxHeads; ++k)
-            if (k < heads.count && row >= heads.row_base[k]) h = k;
-        const int local = row - heads.row_base[h];
-        const int A = heads.num_anchors[h], G = heads.grid[h];
-        const int cell = local / A, a = local % A;
-        const float v = heads.raw[h][((long long)b * G * G + cell) * heads.pitch[h] + a * L + attr];
-        pred[e] = decode_value(v, attr, cell % G, cell / G, heads.anchor_w[h][a], heads.anchor_h[h][a],
-                               heads.stride[h], train);
+        for (int k = 0; k < kMaxHeads - 1; ++k) {
+            const int gg = heads.grid[h] * heads.grid[h];
+            if (h + 1 < heads.count && cell >= gg) {
+                cell -= gg;
+                ++h;
+            }
+        }
+        const int G = heads.grid[h], A = heads.num_anchors[h];
+        const int cx = cell % G, cy = cell / G;
+        const float stride = heads.stride[h];
+        const float* src = heads.raw[h] + ((long long)b * G * G + cell) * heads.pitch[h];
+        float* dst = pred + ((long long)b * N + heads.row_base[h] + (long long)cell * A) * L;
+        const int n = A * L;
+        for (int e = lane; e < n; e += 32) {
+            const int a = e / L, attr = e - a * L;
+            dst[e] = decode_value(__ldg(src + e), attr, cx, cy, heads.anchor_w[h][a], heads.anchor_h[h][a],
+                                  stride, train);
+        }
     }
 }
 
@@ -80,11 +95,13 @@ yolo_decode_heads_kernel(DecodeHeads heads, int B, int N, int L, int train, floa
 
 int launch_decode_heads(const DecodeHeads& heads, int B, int N, int L, int train, float* pred,
                         cudaStream_t stream) {
-    const long long total = (long long)B * N * L;
-    if (total == 0) return RTOD_OK;
-    long long blocks = (total + 255) / 256;
-    if (blocks > (long long)kNumSMs * 32) blocks = (long long)kNumSMs * 32;
-    yolo_decode_heads_kernel<<<(unsigned)blocks, 256, 0, stream>>>(heads, B, N, L, train, pred);
+    int cells = 0;
+    for (int h = 0; h < heads.count; ++h) cells += heads.grid[h] * heads.grid[h];
+    const long long total = (long long)B * cells;                  // one warp each
+    if (total == 0 || N == 0) return RTOD_OK;
+    long long blocks = (total + 7) / 8;
+    if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+    yolo_decode_heads_kernel<<<(unsigned)blocks, 256, 0, stream>>>(heads, B, N, L, train, cells, pred);
     RTOD_LAUNCH_OK("yolo_decode_heads_kernel");
     return RTOD_OK;
 }

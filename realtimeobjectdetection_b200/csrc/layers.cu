@@ -61,6 +61,132 @@ stem_conv3x3_kernel(const float* __restrict__ x, int B, int H, int W, const floa
 }
 
 // ---------------------------------------------------------------------------------------------
+// stem on the warp-level tensor-core path: K = 27 is far too thin for the tcgen05/TMA pipeline
+// (one K step), and the layer is HBM-bound (it writes the largest activation of the network), so
+// each warp builds the im2col fragments of 16 output pixels directly in registers from the NCHW
+// fp32 image, multiplies with register-resident weights via mma.sync.m16n8k16 (fp32 accumulate;
+// image and weights are each split into bf16 hi + lo parts, three products, so the result is
+// fp32-accurate) and stores bf16 NHWC.  The gather of the next tile is issued before the MMAs of
+// the current one.  NT = Cout / 8.
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(128)
+stem_conv3x3_mma_kernel(const float* __restrict__ x, int B, int H, int W, const float* __restrict__ w,
+                        const float* __restrict__ bias, int stride, int pad, int leaky, Act out) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    // the 8 K indices this thread feeds (A and B fragments share them): k = 16*s + 2*t + d + 8*hh,
+    // i = 4*s + 2*hh + d.  krel = offset of the tap relative to the pixel's (c=0, iy0, ix0) element.
+    int krel[8], kdy[8], kdx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int k = 16 * (i >> 2) + 2 * t + (i & 1) + 8 * ((i >> 1) & 1);
+        const int c = k / 9, r = k % 9;
+        kdy[i] = k < 27 ? r / 3 - pad : -100000;             // invalid taps never pass the bounds test
+        kdx[i] = r % 3 - pad;
+        krel[i] = c * H * W + kdy[i] * W + kdx[i];
+    }
+    // B fragments (W[n][k], n = 8*j + g), split w = hi + lo in bf16 so that with the same split of the
+    // image the products hi*hi + lo*hi + hi*lo carry ~16 mantissa bits (the stem stays fp32-accurate)
+    uint32_t bhi[NT][2][2], blo[NT][2][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int k0 = 16 * s + 2 * t + 8 * hh;
+                const float w0 = k0 < 27 ? __ldg(w + (8 * j + g) * 27 + k0) : 0.0f;
+                const float w1 = k0 + 1 < 27 ? __ldg(w + (8 * j + g) * 27 + k0 + 1) : 0.0f;
+                const float h0 = __bfloat162float(__float2bfloat16_rn(w0)), h1 = __bfloat162float(__float2bfloat16_rn(w1));
+                bhi[j][s][hh] = pack_bf16x2(h0, h1);
+                blo[j][s][hh] = pack_bf16x2(w0 - h0, w1 - h1);
+            }
+    float bia[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        bia[j][0] = __ldg(bias + 8 * j + 2 * t);
+        bia[j][1] = __ldg(bias + 8 * j + 2 * t + 1);
+    }
+
+    const int Ho = out.H, Wo = out.W;
+    const long long P = (long long)B * Ho * Wo;
+    const long long n_tiles = (P + 15) / 16;
+    const long long warps = (long long)gridDim.x * 4;
+    __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(out.ptr);
+
+    auto gather = [&](long long tile, float (&v)[16]) {     // rows g and g + 8 of the tile, 8 taps each
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const long long pix = tile * 16 + g + 8 * rr;
+            const bool pv = pix < P;
+            const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho);
+            const long long b = pix / ((long long)Wo * Ho);
+            const int iy0 = oy * stride, ix0 = ox * stride;
+            const float* base = x + b * 3 * H * W + (long long)iy0 * W + ix0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int iy = iy0 + kdy[i], ix = ix0 + kdx[i];
+                v[rr * 8 + i] = (pv && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(base + krel[i]) : 0.0f;
+            }
+        }
+    };
+
+    long long tile = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    float cur[16], nxt[16];
+    if (tile < n_tiles) gather(tile, cur);
+    for (; tile < n_tiles; tile += warps) {
+        if (tile + warps < n_tiles) gather(tile + warps, nxt);            // in flight during the MMAs/stores
+        uint32_t ahi[2][4], alo[2][4];                       // [k step][a0a1, a2a3, a4a5, a6a7]
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const float v0 = cur[rr * 8 + s * 4 + hh * 2], v1 = cur[rr * 8 + s * 4 + hh * 2 + 1];
+                    const float h0 = __bfloat162float(__float2bfloat16_rn(v0));
+                    const float h1 = __bfloat162float(__float2bfloat16_rn(v1));
+                    ahi[s][hh * 2 + rr] = pack_bf16x2(h0, h1);
+                    alo[s][hh * 2 + rr] = pack_bf16x2(v0 - h0, v1 - h1);
+                }
+        float acc[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            acc[j][0] = bia[j][0]; acc[j][1] = bia[j][1]; acc[j][2] = bia[j][0]; acc[j][3] = bia[j][1];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+#define RTOD_MMA(A, Bf)                                                                                      \
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, " \
+                 "{%0,%1,%2,%3};"                                                                            \
+                 : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])                        \
+                 : "r"(A[s][0]), "r"(A[s][1]), "r"(A[s][2]), "r"(A[s][3]), "r"(Bf[j][s][0]), "r"(Bf[j][s][1]))
+                RTOD_MMA(alo, bhi);
+                RTOD_MMA(ahi, blo);
+                RTOD_MMA(ahi, bhi);
+#undef RTOD_MMA
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const long long pix = tile * 16 + g + 8 * rr;
+            if (pix >= P) continue;
+            __nv_bfloat16* dst = obase + pix * out.pitch + 2 * t;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                float v0 = acc[j][2 * rr], v1 = acc[j][2 * rr + 1];
+                if (leaky) {
+                    v0 = leaky01(v0);
+                    v1 = leaky01(v1);
+                }
+                *reinterpret_cast<uint32_t*>(dst + 8 * j) = pack_bf16x2(v0, v1);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // layout converters (plan input when the first layer is not a stem; debug read-back)
 // ---------------------------------------------------------------------------------------------
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, Act out) {
@@ -254,9 +380,18 @@ int launch_stem_conv(const float* x, int B, int Cin, int H, int W, const float* 
     if (Cin != 3 || ks != 3 || Cout % 8 != 0 || Cout > 256 || out.fp32)
         return fail(RTOD_ERR_UNSUPPORTED, "stem conv supports 3x3, Cin=3, Cout%%8==0, Cout<=256");
     const long long pixels = (long long)B * out.H * out.W;
-    stem_conv3x3_kernel<<<ceil_div(pixels, 128), 128, (size_t)Cout * 28 * sizeof(float), stream>>>(
-        x, B, H, W, w, bias, Cout, stride, pad, leaky, out);
-    RTOD_LAUNCH_OK("stem_conv3x3_kernel");
+    long long blocks = (pixels + 63) / 64;                       // 4 warps x 16 pixels per pass
+    if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+    if (Cout == 32)
+        stem_conv3x3_mma_kernel<4><<<(unsigned)blocks, 128, 0, stream>>>(x, B, H, W, w, bias, stride, pad, leaky, out);
+    else if (Cout == 16)
+        stem_conv3x3_mma_kernel<2><<<(unsigned)blocks, 128, 0, stream>>>(x, B, H, W, w, bias, stride, pad, leaky, out);
+    else if (Cout == 64)
+        stem_conv3x3_mma_kernel<8><<<(unsigned)blocks, 128, 0, stream>>>(x, B, H, W, w, bias, stride, pad, leaky, out);
+    else
+        stem_conv3x3_kernel<<<ceil_div(pixels, 128), 128, (size_t)Cout * 28 * sizeof(float), stream>>>(
+            x, B, H, W, w, bias, Cout, stride, pad, leaky, out);
+    RTOD_LAUNCH_OK("stem_conv3x3 kernel");
     return RTOD_OK;
 }
 
