@@ -26,6 +26,7 @@
 // (warp 2 also owns the TMEM allocation).  Every mbarrier wait is bounded: on a time-out the
 // kernel raises *err_flag and drains instead of hanging the GPU.
 #include "conv_tc.cuh"
+#include "tc_ptx.cuh"
 
 #include <cstdlib>
 
@@ -35,146 +36,7 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr int kEpilogueWarps = 4;
-constexpr int kBM = 128;
-constexpr uint32_t kStageTile = 16384;         // epilogue staging tile: 128 rows x 128 B
-constexpr uint32_t kSmemLimit = 225 * 1024;    // dynamic shared memory per CTA (one CTA per SM)
 constexpr uint32_t kResidentLimit = 100 * 1024; // largest weight matrix kept resident in shared memory
-constexpr unsigned long long kWaitTimeoutNs = 2000000000ull;
-
-// ---- PTX wrappers ---------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return done != 0;
-}
-// bounded wait: false after a time-out or once another CTA has raised the failure flag
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
-    if (mbar_try_wait(bar, parity)) return true;
-    if (*(volatile int*)err_flag != 0) return false;
-    const unsigned long long t0 = global_timer_ns();
-    unsigned spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 255u) == 0u) {
-            if (*(volatile int*)err_flag != 0) return false;
-            if (global_timer_ns() - t0 > kWaitTimeoutNs) {
-                atomicExch(err_flag, 2);
-                return false;
-            }
-        }
-    }
-    return true;
-}
-
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
-                                            int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap* map, uint64_t* bar,
-                                                   int c, int w, int h, int n, uint16_t off_w,
-                                                   uint16_t off_h) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
-                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_1() {      // all but the newest group have read their smem
-    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier(int id) {      // the 128 epilogue threads only
-    asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)),
-                 "r"(cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                          uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                     smem_u32(bar))
-                 : "memory");
-}
-// byte offset of 16-byte chunk j of row r inside a TMA-swizzled staging tile whose rows are
-// row_bytes (64 or 128) wide: the chunk index is XORed with address bits [7, ...)
-__device__ __forceinline__ uint32_t staged_offset(int r, int j, uint32_t row_bytes) {
-    const uint32_t sw = row_bytes == 128 ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
-    return (uint32_t)r * row_bytes + (((uint32_t)j ^ sw) << 4);
-}
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// shared-memory matrix descriptor, K-major operand whose rows are one swizzle span wide
-// (row_bytes = 32/64/128): start address, SBO = 8 rows, version 1, swizzle mode
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t row_bytes) {
-    const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
-    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((8u * row_bytes) >> 4) << 32) |
-           (1ull << 46) | (layout << 61);
-}
 
 // =============================================================================================
 // Persistent: one CTA per SM walks output tiles (m fastest, so concurrently running CTAs share the
@@ -410,30 +272,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
 }
 
-// ---- host: tensor-map encoding through the driver entry points (no libcuda link dependency) ---
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
-                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int driver_fn(const char* name, void** fn) {
-    cudaDriverEntryPointQueryResult q;
-    RTOD_CUDA_OK(cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q));
-    if (q != cudaDriverEntryPointSuccess || !*fn)
-        return fail(RTOD_ERR_CUDA, "driver entry point %s unavailable", name);
-    return RTOD_OK;
-}
-
-CUtensorMapSwizzle swizzle_for(int bk) {
-    return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-}
-
-int pick_bk(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : (cin % 16 == 0 ? 16 : 0)); }
-
 }  // namespace
 
 bool conv_tc_supported(const ConvArgs& a) {
@@ -451,6 +289,8 @@ bool conv_tc_supported(const ConvArgs& a) {
 
 int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     if (!conv_tc_supported(a)) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: unsupported convolution shape");
+    launch->patch = 0;
+    if (conv_patch_eligible(a)) return conv_patch_prepare(a, err_flag, launch);
     static EncodeTiledFn encode_tiled = nullptr;
     static EncodeIm2colFn encode_im2col = nullptr;
     if (!encode_tiled) {
@@ -463,6 +303,10 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     const int BK = pick_bk(a.Cin);
     int BN = a.Cout_pad < 256 ? a.Cout_pad : 256;       // widest tile the single-CTA MMA supports
     if (a.Cout_pad % BN != 0) BN = 128;
+    if (const char* e = getenv("RTOD_TC_BN")) {          // tuning knob
+        const int v = atoi(e);
+        if (v >= 32 && v <= BN && a.Cout_pad % v == 0) BN = v;
+    }
     if (a.Cout_pad % BN != 0 || BN % 32 != 0)
         return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: Cout_pad %d not tileable", a.Cout_pad);
     const long long M = (long long)a.B * a.out.H * a.out.W;
@@ -498,6 +342,10 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
         stage_bytes_eff = (uint32_t)kBM * BK * 2;
     }
     int stages = (int)((kSmemLimit - fixed) / stage_bytes_eff);
+    if (const char* e = getenv("RTOD_TC_STAGES")) {      // tuning knob
+        const int v = atoi(e);
+        if (v >= 2 && v < stages) stages = v;
+    }
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     p.stages = stages;
@@ -579,6 +427,7 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
 }
 
 int conv_tc_launch(const ConvTcLaunch& launch, cudaStream_t stream) {
+    if (launch.patch) return conv_patch_launch(launch, stream);
     conv_tc_kernel<<<launch.grid, kThreads, launch.smem_bytes, stream>>>(launch.p);
     RTOD_LAUNCH_OK("conv_tc_kernel");
     return RTOD_OK;

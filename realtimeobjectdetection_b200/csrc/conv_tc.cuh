@@ -27,11 +27,39 @@ struct alignas(64) ConvTcParams {
     uint32_t idesc;             // tcgen05 instruction descriptor (bf16 x bf16 -> fp32, M=128, N=BN)
 };
 
+// 3x3 / stride 1 / pad 1 convolutions: "halo patch" variant (conv_patch.cu).  One TMA tiled load
+// brings a (TH+2) x (TW+2) pixel patch of a 16/32/64-channel slice; the nine filter taps are nine
+// row-shifted views of that patch (UMMA descriptors may start at any 128-byte row of a swizzled
+// tile), so the activations are fetched once instead of nine times.
+struct alignas(64) ConvPatchParams {
+    CUtensorMap tmA;            // input: 4-D tiled {C, W, H, N}, box {BK, PW, PH, 1}
+    CUtensorMap tmB;            // weights: 2-D tiled {K, Cout_pad}, box {BK, BN}
+    CUtensorMap tmOut;          // output: 4-D tiled {Cout, W, H, N}, box {ecols, TW, TH, 1}
+    CUtensorMap tmRes;          // shortcut operand, same box (valid iff has_res)
+    const float* bias;
+    int* err_flag;
+    int has_res, b_resident, leaky;
+    int ecols, BK, BN, cchunks;
+    int TW, TH, PW, PH;         // output tile, input patch (PW = TW + 2, PH = TH + 2)
+    int tiles_x, tiles_y, m_tiles, total_tiles;
+    int a_bufs, b_stages;       // patch buffers in flight, weight ring depth
+    uint32_t a_buf_bytes;       // one patch buffer (rows 0 .. 128 + 2*PW + 2), 1024-aligned
+    int tmem_cols;
+    uint32_t idesc;
+};
+
 struct ConvTcLaunch {           // host side: kernel parameters + launch geometry
     ConvTcParams p;
+    ConvPatchParams pp;
+    int patch;                  // 1: launch conv_patch_kernel(pp), 0: conv_tc_kernel(p)
     dim3 grid;
     uint32_t smem_bytes;
 };
+
+// conv_patch.cu
+bool conv_patch_eligible(const ConvArgs& a);
+int conv_patch_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch);
+int conv_patch_launch(const ConvTcLaunch& launch, cudaStream_t stream);
 
 // true if the tensor-core kernel tiles this convolution
 bool conv_tc_supported(const ConvArgs& a);
