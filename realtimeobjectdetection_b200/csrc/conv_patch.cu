@@ -105,13 +105,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
             const uint32_t a_tx = (uint32_t)p.PH * p.PW * row_bytes;
             int buf = 0;
             uint32_t aphase = 0;
-            for (int q = 0; q < Q; ++q) {
+            int n = 0, y0 = 0, x0 = 0, n0 = 0, cc = p.cchunks, local = -1;
+            for (int q = 0; q < Q; ++q, ++cc) {
+                if (cc == p.cchunks) {                       // next tile
+                    cc = 0;
+                    tile_coords(++local, n, y0, x0, n0);
+                }
                 if (!mbar_wait(&a_empty[buf], aphase ^ 1u, p.err_flag)) break;
-                int n, y0, x0, n0;
-                tile_coords(q / p.cchunks, n, y0, x0, n0);
                 mbar_expect_tx(&a_full[buf], a_tx);
-                tma_load_4d(a_buf + (size_t)buf * p.a_buf_bytes, &p.tmA, &a_full[buf], (q % p.cchunks) * p.BK,
-                            x0 - 1, y0 - 1, n);
+                tma_load_4d(a_buf + (size_t)buf * p.a_buf_bytes, &p.tmA, &a_full[buf], cc * p.BK, x0 - 1, y0 - 1, n);
                 if (++buf == p.a_bufs) {
                     buf = 0;
                     aphase ^= 1u;
@@ -132,12 +134,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
                 for (int local = 0; ok && local < my_tiles; ++local) {
                     int n, y0, x0, n0;
                     tile_coords(local, n, y0, x0, n0);
-                    for (int cc = 0; ok && cc < p.cchunks; ++cc)
-                        for (int tap = 0; tap < 9; ++tap) {
+                    const int cin = p.cchunks * p.BK;
+                    for (int c0 = 0; ok && c0 < cin; c0 += p.BK)
+                        for (int tap = 0, k0 = c0; tap < 9; ++tap, k0 += cin) {      // k0 = tap*Cin + c0
                             if (!mbar_wait(&b_empty[bs], bphase ^ 1u, p.err_flag)) { ok = false; break; }
                             mbar_expect_tx(&b_full[bs], b_bytes);
-                            tma_load_2d(b_buf + (size_t)bs * b_bytes, &p.tmB, &b_full[bs],
-                                        (tap * p.cchunks + cc) * p.BK, n0);
+                            tma_load_2d(b_buf + (size_t)bs * b_bytes, &p.tmB, &b_full[bs], k0, n0);
                             if (++bs == p.b_stages) {
                                 bs = 0;
                                 bphase ^= 1u;
@@ -152,6 +154,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
             bool ok = true;
             int bs = 0, ab = 0;
             uint32_t bphase = 0, aphase = 0;
+            const uint64_t desc_tmpl = smem_desc(0u, row_bytes);
+            const uint32_t a_base = smem_u32(a_buf), b_base = smem_u32(b_buf);
+            const int ksteps = p.BK / 16;
+            const uint32_t row_step = (uint32_t)(p.PW - 3) * row_bytes;     // from tap (ky,2) to tap (ky+1,0)
             if (p.b_resident) ok = mbar_wait(wres_bar, 0u, p.err_flag);
             for (int local = 0; ok && local < my_tiles; ++local) {
                 const int buf = local & 1;
@@ -160,27 +166,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.BN);
                 for (int cc = 0; ok && cc < p.cchunks; ++cc) {
                     if (!mbar_wait(&a_full[ab], aphase, p.err_flag)) { ok = false; break; }
-                    const uint32_t patch = smem_u32(a_buf + (size_t)ab * p.a_buf_bytes);
-                    for (int tap = 0; tap < 9; ++tap) {
+                    // tap (ky, kx) = the patch viewed from row ky*PW + kx on: the A descriptor's start
+                    // address walks through the patch by additions only
+                    uint32_t a_addr = a_base + (uint32_t)ab * p.a_buf_bytes;
+                    uint32_t b_res = b_base + (uint32_t)cc * b_bytes;       // resident: tile (tap*cchunks + cc)
+                    for (int tap = 0, kx = 0; tap < 9; ++tap) {
                         uint32_t b_addr;
                         if (p.b_resident) {
-                            b_addr = smem_u32(b_buf + (size_t)(tap * p.cchunks + cc) * b_bytes);
+                            b_addr = b_res;
+                            b_res += (uint32_t)p.cchunks * b_bytes;
                         } else {
                             if (!mbar_wait(&b_full[bs], bphase, p.err_flag)) { ok = false; break; }
-                            b_addr = smem_u32(b_buf + (size_t)bs * b_bytes);
+                            b_addr = b_base + (uint32_t)bs * b_bytes;
                         }
                         tc_fence_after();
-                        // tap (ky, kx) = the patch viewed from row ky*PW + kx on
-                        const uint32_t a_addr = patch + (uint32_t)((tap / 3) * p.PW + tap % 3) * row_bytes;
-                        for (int k = 0; k < p.BK / 16; ++k)
-                            umma_bf16(tmem_acc, smem_desc(a_addr + k * 32, row_bytes), smem_desc(b_addr + k * 32, row_bytes),
-                                      p.idesc, (uint32_t)(cc | tap | k));
+                        uint64_t da = desc_tmpl | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+                        uint64_t db = desc_tmpl | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
+                        for (int k = 0; k < ksteps; ++k, da += 2, db += 2)
+                            umma_bf16(tmem_acc, da, db, p.idesc, (uint32_t)(cc | tap | k));
                         if (!p.b_resident) {
                             umma_commit(&b_empty[bs]);
                             if (++bs == p.b_stages) {
                                 bs = 0;
                                 bphase ^= 1u;
                             }
+                        }
+                        if (++kx == 3) {
+                            kx = 0;
+                            a_addr += row_bytes + row_step;
+                        } else {
+                            a_addr += row_bytes;
                         }
                     }
                     umma_commit(&a_empty[ab]);               // patch buffer free once these MMAs retire
@@ -316,7 +331,12 @@ PatchTile pick_tile(int H, int W) {
 }  // namespace
 
 bool conv_patch_eligible(const ConvArgs& a) {
-    if (getenv("RTOD_TC_NO_PATCH")) return false;
+    // Opt-in (RTOD_TC_PATCH=1 for resident-weight layers, RTOD_TC_PATCH_ALL=1 for every 3x3/s1 layer):
+    // on B200 the weight stream, not the activation gather, bounds these layers, so with one CTA per
+    // pair of tiles the 19 % of MMA rows lost to the halo columns outweigh the saved traffic
+    // (measured: 129 vs 96 us on the 26x26x512 layers).  It becomes the default once the weight
+    // stream is halved by cta_group::2 pairs.
+    if (!getenv("RTOD_TC_PATCH") && !getenv("RTOD_TC_PATCH_ALL")) return false;
     if (a.ks != 3 || a.stride != 1 || a.pad != 1 || a.out.fp32) return false;
     if (a.out.H != a.in.H || a.out.W != a.in.W) return false;
     if (pick_tile(a.out.H, a.out.W).eff < 0.70) return false;   // small maps tile badly: im2col kernel

@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ring stages hold {A, B} tiles, or A tiles only when the whole weight matrix is resident
     uint8_t* b_resident = smem + (size_t)p.stages * stage_bytes;         // [num_kb][BN x BK] iff p.b_resident
     uint8_t* out_stage = b_resident + (p.b_resident ? (size_t)p.ks * p.ks * p.cchunks * b_bytes : 0);
-    uint8_t* res_stage = out_stage + 2 * kStageTile;                     // [2][kStageTile] shortcut operand
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(res_stage + (p.has_res ? 2 * kStageTile : 0));
+    uint8_t* res_stage = out_stage + p.stage_bufs * kStageTile;          // [stage_bufs][kStageTile] shortcut operand
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(res_stage + (p.has_res ? p.stage_bufs * kStageTile : 0));
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* acc_full = empty_bar + p.stages;          // [2] MMA -> epilogue
     uint64_t* acc_empty = acc_full + 2;                 // [2] epilogue -> MMA
@@ -110,20 +110,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     oh = ((m0 / p.Wo) % p.Ho) * p.stride - p.pad;
                     on = m0 / (p.Wo * p.Ho);
                 }
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag)) { ok = false; break; }
-                    uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
-                    mbar_expect_tx(&full_bar[stage], stage_bytes);
-                    const int tap = kb / p.cchunks, c0 = (kb - tap * p.cchunks) * p.BK;
-                    if (p.ks > 1)
-                        tma_load_im2col_4d(a_dst, &p.tmA, &full_bar[stage], c0, ow, oh, on,
-                                           (uint16_t)(tap % p.ks), (uint16_t)(tap / p.ks));
-                    else
-                        tma_load_2d(a_dst, &p.tmA, &full_bar[stage], c0, m0);
-                    if (!p.b_resident) tma_load_2d(a_dst + a_bytes, &p.tmB, &full_bar[stage], kb * p.BK, n0);
-                    if (++stage == p.stages) {
-                        stage = 0;
-                        phase ^= 1u;
+                // taps outer, channel slices inner: all coordinates advance by additions (a lone
+                // thread retires one dependent instruction every ~5 cycles: divisions here would
+                // cost more than the tensor core needs for the whole k-block)
+                int k0 = 0;
+                for (int tap = 0; ok && tap < p.ks * p.ks; ++tap) {
+                    const uint16_t off_w = (uint16_t)(tap % p.ks), off_h = (uint16_t)(tap / p.ks);
+                    for (int c0 = 0; c0 < p.cchunks * p.BK; c0 += p.BK, k0 += p.BK) {
+                        if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag)) { ok = false; break; }
+                        uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
+                        mbar_expect_tx(&full_bar[stage], stage_bytes);
+                        if (p.ks > 1) tma_load_im2col_4d(a_dst, &p.tmA, &full_bar[stage], c0, ow, oh, on, off_w, off_h);
+                        else tma_load_2d(a_dst, &p.tmA, &full_bar[stage], c0, m0);
+                        if (!p.b_resident) tma_load_2d(a_dst + a_bytes, &p.tmB, &full_bar[stage], k0, n0);
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
                     }
                 }
             }
@@ -135,6 +138,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             uint32_t phase = 0;
             bool ok = true;
             int local = 0;
+            const uint64_t desc_tmpl = smem_desc(0u, row_bytes);
+            const uint32_t ring_base = smem_u32(smem), wres_base = smem_u32(b_resident);
+            const int ksteps = p.BK / 16;
             if (p.b_resident) ok = mbar_wait(wres_bar, 0u, p.err_flag);
             for (int tile = blockIdx.x; ok && tile < p.total_tiles; tile += gridDim.x, ++local) {
                 const int buf = local & 1;
@@ -145,11 +151,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 for (int kb = 0; kb < num_kb; ++kb) {
                     if (!mbar_wait(&full_bar[stage], phase, p.err_flag)) { ok = false; break; }
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t b_addr = p.b_resident ? smem_u32(b_resident + (size_t)kb * b_bytes) : a_addr + a_bytes;
-                    for (int k = 0; k < p.BK / 16; ++k)
-                        umma_bf16(tmem_acc, smem_desc(a_addr + k * 32, row_bytes),
-                                  smem_desc(b_addr + k * 32, row_bytes), p.idesc, (uint32_t)(kb | k));
+                    // descriptors differ from the template only in the 14-bit start-address field
+                    const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
+                    const uint32_t b_addr = p.b_resident ? wres_base + (uint32_t)kb * b_bytes : a_addr + a_bytes;
+                    uint64_t da = desc_tmpl | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+                    uint64_t db = desc_tmpl | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
+                    for (int k = 0; k < ksteps; ++k, da += 2, db += 2)      // +32 bytes per K=16 step
+                        umma_bf16(tmem_acc, da, db, p.idesc, (uint32_t)(kb | k));
                     umma_commit(&empty_bar[stage]);          // frees the stage when the MMAs retire
                     if (++stage == p.stages) {
                         stage = 0;
@@ -171,17 +179,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int ecols = p.ecols;
         const uint32_t erow = (uint32_t)ecols * (p.out_fp32 ? 4u : 2u);
         const int n_chunks = p.BN / ecols;
+        const uint32_t sbufs = (uint32_t)p.stage_bufs;       // staging tiles in flight: 2, or 1 to save smem
         auto issue_res = [&](uint32_t g) {                   // leader only
             const int tl = (int)(g / (uint32_t)n_chunks), c = (int)(g - (uint32_t)tl * n_chunks);
             const int t = blockIdx.x + tl * gridDim.x;
             if (t >= p.total_tiles) return;
-            mbar_expect_tx(&res_full[g & 1], kBM * erow);
-            tma_load_2d(res_stage + (g & 1) * kStageTile, &p.tmRes, &res_full[g & 1],
+            const uint32_t sb = sbufs == 2 ? (g & 1u) : 0u;
+            mbar_expect_tx(&res_full[sb], kBM * erow);
+            tma_load_2d(res_stage + sb * kStageTile, &p.tmRes, &res_full[sb],
                         (t / p.m_tiles) * p.BN + c * ecols, (t % p.m_tiles) * kBM);
         };
         if (p.has_res && leader) {
             issue_res(0);
-            issue_res(1);
+            if (sbufs == 2) issue_res(1);
         }
         // NOTE: no early exit in this role: the named barriers below must be reached by all 128
         // threads the same number of times.  After a time-out (*err_flag != 0) every wait returns
@@ -196,11 +206,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.BN) + ((uint32_t)(quarter * 32) << 16);
             for (int c = 0; c < n_chunks; ++c, ++g) {
-                uint8_t* ostage = out_stage + (g & 1) * kStageTile;
-                const uint8_t* rstage = res_stage + (g & 1) * kStageTile;
-                if (leader) bulk_wait_read_1();              // the store that last used ostage has drained
+                const uint32_t sb = sbufs == 2 ? (g & 1u) : 0u;
+                uint8_t* ostage = out_stage + sb * kStageTile;
+                const uint8_t* rstage = res_stage + sb * kStageTile;
+                if (leader) {                                // the store that last used ostage has drained
+                    if (sbufs == 2) bulk_wait_read_1();
+                    else bulk_wait_read_0();
+                }
                 epi_barrier(1);
-                if (p.has_res) mbar_wait(&res_full[g & 1], (g >> 1) & 1u, p.err_flag);
+                if (p.has_res) mbar_wait(&res_full[sb], (sbufs == 2 ? (g >> 1) : g) & 1u, p.err_flag);
                 const int halves = p.out_fp32 ? 1 : (ecols + 31) / 32;      // 32 accumulator columns each
                 for (int h = 0; h < halves; ++h) {
                     uint32_t v[32];
@@ -257,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 if (leader) {
                     tma_store_2d(&p.tmOut, ostage, n0 + c * ecols, m0);   // rows >= M / cols >= Cout are clipped
                     bulk_commit();
-                    if (p.has_res) issue_res(g + 2);
+                    if (p.has_res) issue_res(g + sbufs);
                 }
             }
         }
@@ -332,16 +346,40 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     const uint32_t stage_bytes = (uint32_t)(kBM + BN) * BK * 2;
     p.has_res = a.res != nullptr;
     p.ecols = a.out.fp32 ? 32 : (BN < 64 ? BN : 64);
-    uint32_t fixed = 1024 /*alignment slack*/ + 2 * kStageTile + (p.has_res ? 2 * kStageTile : 0) + 512;
-    // small layers: keep the whole weight matrix in shared memory and stream activations only
+    // ---- shared-memory plan --------------------------------------------------------------------
+    // Measured on B200: the TMA/mbarrier round trips of ONE CTA serialise (~250+ cycles per TMA
+    // operation whatever its size) while those of different CTAs on an SM overlap.  Tiles with
+    // little MMA work per TMA operation therefore run 2-4 CTAs per SM (TMEM: 2*BN columns each),
+    // with a single staging tile and without resident weights if that is what makes them fit;
+    // fat tiles (BN = 256) keep one CTA per SM and the deepest operand ring that fits.
     const uint32_t w_bytes = (uint32_t)BN * a.K * 2;
-    p.b_resident = (a.Cout_pad == BN && w_bytes <= kResidentLimit && getenv("RTOD_TC_NO_RESIDENT") == nullptr) ? 1 : 0;
-    uint32_t stage_bytes_eff = stage_bytes;
-    if (p.b_resident) {
-        fixed += w_bytes;
-        stage_bytes_eff = (uint32_t)kBM * BK * 2;
+    const bool may_reside = a.Cout_pad == BN && w_bytes <= kResidentLimit && getenv("RTOD_TC_NO_RESIDENT") == nullptr;
+    const uint32_t a_stage = (uint32_t)kBM * BK * 2;
+    int max_ctas = 512 / cols;
+    if (const char* e = getenv("RTOD_TC_CTAS")) { const int v = atoi(e); if (v >= 1 && v < max_ctas) max_ctas = v; }
+    if (max_ctas > 3) max_ctas = 3;                      // measured: 3 beats 2 and 4 on the 208x208 layers
+    int ctas_per_sm = 1, stages = 0;
+    uint32_t fixed = 0, stage_bytes_eff = stage_bytes;
+    for (int ctas = max_ctas; ctas >= 1 && stages == 0; --ctas) {
+        const uint32_t cap = ctas == 1 ? kSmemLimit : (227u * 1024u) / ctas - 2048u;
+        for (int opt = 0; opt < 4 && stages == 0; ++opt) {          // prefer: resident + 2 staging tiles
+            const bool resident = may_reside && (opt & 1) == 0;
+            const int sbufs = (opt & 2) ? 1 : 2;
+            if ((opt & 1) && may_reside == false) continue;
+            if (ctas == 1 && sbufs == 1) continue;
+            const uint32_t fx = 1024 + sbufs * kStageTile * (p.has_res ? 2 : 1) + 512 + (resident ? w_bytes : 0);
+            const uint32_t sb = resident ? a_stage : stage_bytes;
+            const int want = ctas == 1 ? 2 : 3;
+            if (fx + want * sb > cap) continue;
+            ctas_per_sm = ctas;
+            p.b_resident = resident ? 1 : 0;
+            p.stage_bufs = sbufs;
+            fixed = fx;
+            stage_bytes_eff = sb;
+            stages = (int)((cap - fx) / sb);
+        }
     }
-    int stages = (int)((kSmemLimit - fixed) / stage_bytes_eff);
+    if (stages == 0) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: shared memory budget exceeded");
     if (const char* e = getenv("RTOD_TC_STAGES")) {      // tuning knob
         const int v = atoi(e);
         if (v >= 2 && v < stages) stages = v;
@@ -352,7 +390,7 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     p.m_tiles = (int)((M + kBM - 1) / kBM);
     p.total_tiles = p.m_tiles * (a.Cout_pad / BN);
     launch->smem_bytes = stages * stage_bytes_eff + fixed;
-    launch->grid = dim3((unsigned)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs), 1, 1);
+    launch->grid = dim3((unsigned)(p.total_tiles < kNumSMs * ctas_per_sm ? p.total_tiles : kNumSMs * ctas_per_sm), 1, 1);
 
     // ---- A ----
     const cuuint32_t estr1[4] = {1, 1, 1, 1};

@@ -16,6 +16,7 @@ struct alignas(64) ConvTcParams {
     int* err_flag;              // device-side failure flag (pipeline time-out)
     int out_fp32, has_res;
     int b_resident;             // whole [BN x K] weight matrix lives in smem (single N tile, small K*BN)
+    int stage_bufs;             // epilogue staging tiles in flight (2; 1 when several CTAs share an SM)
     int ecols;                  // channels per epilogue chunk (one staging row: 64 bf16 / 32 fp32)
     int M, Cout;                // output pixels, real channels
     int leaky;

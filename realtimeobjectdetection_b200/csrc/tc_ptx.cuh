@@ -10,7 +10,7 @@ namespace rtod {
 constexpr unsigned long long kWaitTimeoutNs = 2000000000ull;   // bounded mbarrier waits: 2 s
 constexpr int kBM = 128;                                       // UMMA M (rows of one accumulator)
 constexpr uint32_t kStageTile = 16384;                         // epilogue staging tile: 128 rows x 128 B
-constexpr uint32_t kSmemLimit = 225 * 1024;                    // dynamic shared memory per CTA
+constexpr uint32_t kSmemLimit = 226 * 1024 + 512;                    // dynamic shared memory per CTA
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 static __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -79,6 +79,7 @@ static __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bu
 static __device__ __forceinline__ void bulk_wait_read_1() {      // all but the newest group have read their smem
     asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
+static __device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 static __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 static __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 static __device__ __forceinline__ void epi_barrier(int id) {      // the 128 epilogue threads only
