@@ -371,6 +371,15 @@ def run_b200(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    # libraries (NCCL's version banner) write to stdout: keep fd 1 for the one JSON line
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*args, **kwargs):                                 # noqa: A001
+        sys.stdout.flush()
+        os.write(_real_stdout, (" ".join(str(x) for x in args) + "\n").encode())
+
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -317,6 +317,10 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     const int BK = pick_bk(a.Cin);
     int BN = a.Cout_pad < 256 ? a.Cout_pad : 256;       // widest tile the single-CTA MMA supports
     if (a.Cout_pad % BN != 0) BN = 128;
+    {   // small batches: a layer must still spread over the 148 SMs -> narrower N tiles
+        const long long m_tiles = ((long long)a.B * a.out.H * a.out.W + kBM - 1) / kBM;
+        while (BN > 32 && m_tiles * (a.Cout_pad / BN) < 120 && a.Cout_pad % (BN / 2) == 0) BN /= 2;
+    }
     if (const char* e = getenv("RTOD_TC_BN")) {          // tuning knob
         const int v = atoi(e);
         if (v >= 32 && v <= BN && a.Cout_pad % v == 0) BN = v;
