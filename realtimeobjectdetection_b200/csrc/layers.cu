@@ -6,6 +6,8 @@
 // src/darknet.py:316-410).  All of them are HBM-bound: 16-byte vector accesses, one pass.
 #include "layers.cuh"
 
+#include <cstdlib>
+
 namespace rtod {
 
 namespace {
@@ -379,6 +381,10 @@ int launch_stem_conv(const float* x, int B, int Cin, int H, int W, const float* 
                      int Cout, int ks, int stride, int pad, int leaky, Act out, cudaStream_t stream) {
     if (Cin != 3 || ks != 3 || Cout % 8 != 0 || Cout > 256 || out.fp32)
         return fail(RTOD_ERR_UNSUPPORTED, "stem conv supports 3x3, Cin=3, Cout%%8==0, Cout<=256");
+    // stride-1 stems (both reference networks): TMA-staged strips, see stem.cu
+    if (getenv("RTOD_STEM_NO_TMA") == nullptr && stride == 1 && pad == 1 && W % 4 == 0 && W >= 64 && (Cout == 16 || Cout == 32 || Cout == 64) &&
+        (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && out.H == H && out.W == W)
+        return launch_stem_tma(x, B, H, W, w, bias, Cout, leaky, out, stream);
     const long long pixels = (long long)B * out.H * out.W;
     long long blocks = (pixels + 63) / 64;                       // 4 warps x 16 pixels per pass
     if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;

@@ -27,6 +27,8 @@ struct ConvArgs {
 int launch_stem_conv(const float* x_nchw, int B, int Cin, int H, int W, const float* w_f32,
                      const float* bias, int Cout, int ks, int stride, int pad, int leaky, Act out,
                      cudaStream_t stream);
+int launch_stem_tma(const float* x_nchw, int B, int H, int W, const float* w_f32, const float* bias, int Cout,
+                    int leaky, Act out, cudaStream_t stream);   // stem.cu
 int launch_nchw_to_nhwc(const float* x_nchw, int B, Act out, cudaStream_t stream);
 int launch_nhwc_to_nchw(Act in, int B, float* out_nchw, cudaStream_t stream);
 int launch_maxpool(Act in, Act out, int B, int size, int stride, cudaStream_t stream);

@@ -1,0 +1,215 @@
+// stem.cu -- the first convolution block (src/darknet.py:488-501 with Cin = 3: 3x3, stride 1, pad 1,
+// BatchNorm folded, leaky 0.1) straight from the NCHW fp32 image to NHWC bf16.
+//
+// HBM-bound by construction (it writes the largest activation of the network: B*H*W*Cout bf16), so
+// the design is about never waiting on memory: persistent CTAs walk "strips" (one output row segment
+// of <= 240 pixels of one image); a 3-D TMA tiled load (box {SW+8, 3 rows, 3 channels}, halo and
+// image border zero-filled by the TMA bounds check) stages the 3x3 neighbourhood of a whole strip in
+// shared memory four strips ahead; each warp then builds the im2col fragments of 16 pixels from
+// shared memory (no bounds checks, no global latency) and multiplies with register-resident weights
+// on the warp-level tensor-core path (mma.sync m16n8k16, fp32 accumulate).  K = 27 is one K-step:
+// the tcgen05/TMEM pipeline has nothing to pipeline here.  The image is split into bf16 hi + lo parts
+// (two MMAs), the weights are bf16 like every other layer's.
+#include <cstdlib>
+
+#include "layers.cuh"
+#include "tc_ptx.cuh"
+
+namespace rtod {
+
+namespace {
+
+constexpr int kStemStages = 4;
+
+struct StemParams {
+    CUtensorMap tmX;          // {W, H, 3*B} fp32, box {box_w, 3, 3}
+    const float* w;           // [Cout][27] fp32, BN folded
+    const float* bias;
+    int* err_flag_unused;
+    Act out;
+    int B, H, W, leaky;
+    int SW, box_w, strips_per_row, total_strips, tiles_per_strip;
+    int dbg;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(512) stem_tma_kernel(const __grid_constant__ StemParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_addr + 127u) & ~127u) - raw_addr);
+    const uint32_t stage_bytes = (uint32_t)9 * p.box_w * 4;            // multiple of 16 (box_w % 4 == 0)
+    const uint32_t stage_pitch = (stage_bytes + 127u) & ~127u;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStemStages * stage_pitch);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int nwarps = blockDim.x >> 5;
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&p.tmX);
+        for (int s = 0; s < kStemStages; ++s) mbar_init(&full[s], 1);
+        *reinterpret_cast<uint32_t*>(full + kStemStages) = 0u;         // the zero word padding taps read
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // tap offsets inside a stage for the 8 K indices this thread feeds: k = 16*s + 2*t + d + 8*hh
+    // byte offsets inside a stage; the five padding taps (k >= 27) read a zero word kept behind the barriers
+    uint32_t koff[8];
+    uint32_t* zero_word = reinterpret_cast<uint32_t*>(full + kStemStages);
+    const uint32_t smem_base = smem_u32(smem), zero_addr = smem_u32(zero_word);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int k = 16 * (i >> 2) + 2 * t + (i & 1) + 8 * ((i >> 1) & 1);
+        koff[i] = k < 27 ? (uint32_t)((k / 3) * p.box_w + (k % 3) + 3) * 4u : 0xFFFFFFFFu;   // (c*3+ky)*box_w + kx + 3
+    }
+    uint32_t bfr[NT][2][2];                              // B fragments: W[n = 8j + g][k], bf16 like every layer's weights
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int k0 = 16 * s + 2 * t + 8 * hh;
+                const float w0 = k0 < 27 ? __ldg(p.w + (8 * j + g) * 27 + k0) : 0.0f;
+                const float w1 = k0 + 1 < 27 ? __ldg(p.w + (8 * j + g) * 27 + k0 + 1) : 0.0f;
+                bfr[j][s][hh] = pack_bf16x2(w0, w1);
+            }
+    float bia[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        bia[j][0] = __ldg(p.bias + 8 * j + 2 * t);
+        bia[j][1] = __ldg(p.bias + 8 * j + 2 * t + 1);
+    }
+
+    auto issue = [&](int local) {                     // thread 0: strip `local` of this CTA -> stage local % S
+        const int strip = blockIdx.x + local * gridDim.x;
+        if (strip >= p.total_strips || p.dbg == 1) return;
+        const int seg = strip % p.strips_per_row;
+        const int y = (strip / p.strips_per_row) % p.H;
+        const int b = strip / (p.strips_per_row * p.H);
+        const int s = local % kStemStages;
+        mbar_expect_tx(&full[s], stage_bytes);
+        // the innermost start coordinate must be 16-byte aligned: start 4 columns (not 1) left of the strip,
+        // so shared-memory column j holds image column seg*SW - 4 + j
+        tma_load_3d(smem + s * stage_pitch, &p.tmX, &full[s], seg * p.SW - 4, y - 1, 3 * b);
+    };
+    if (threadIdx.x == 0)
+        for (int l = 0; l < kStemStages - 1; ++l) issue(l);
+
+    __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out.ptr);
+    for (int local = 0;; ++local) {
+        const int strip = blockIdx.x + local * gridDim.x;
+        if (strip >= p.total_strips) break;
+        const int s = local % kStemStages;
+        // stage (local + S - 1) % S was consumed in the previous iteration (all warps passed its barrier)
+        if (threadIdx.x == 0) issue(local + kStemStages - 1);
+        if (p.dbg != 1) {
+            const uint32_t parity = (uint32_t)(local / kStemStages) & 1u;
+            unsigned spins = 0;
+            while (!mbar_try_wait(&full[s], parity))
+                if (++spins > (1u << 26)) break;     // never in practice; avoids a hard hang
+        }
+        const int seg = strip % p.strips_per_row;
+        const int y = (strip / p.strips_per_row) % p.H;
+        const int b = strip / (p.strips_per_row * p.H);
+        const float* st = reinterpret_cast<const float*>(smem + s * stage_pitch);
+        const int x_first = seg * p.SW;
+        for (int tile = warp; tile < p.tiles_per_strip && p.dbg != 2; tile += nwarps) {
+            const int px0 = tile * 16;
+            if (x_first + px0 >= p.W) break;
+            uint32_t ahi[2][4], alo[2][4];
+            const uint32_t stage_addr = smem_base + (uint32_t)s * stage_pitch + (uint32_t)(px0 + g) * 4u;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                    float v0, v1;
+                    const uint32_t a0 = koff[i] == 0xFFFFFFFFu ? zero_addr : stage_addr + rr * 32u + koff[i];
+                    const uint32_t a1 = koff[i + 1] == 0xFFFFFFFFu ? zero_addr : stage_addr + rr * 32u + koff[i + 1];
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(a0));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(a1));
+                    // image = hi + lo in bf16: two MMAs keep ~16 mantissa bits of the pixels
+                    const uint32_t hi = pack_bf16x2(v0, v1);
+                    ahi[i >> 2][((i >> 1) & 1) * 2 + rr] = hi;
+                    alo[i >> 2][((i >> 1) & 1) * 2 + rr] = pack_bf16x2(v0 - bf16_lo(hi), v1 - bf16_hi(hi));
+                }
+            float acc[NT][4];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                acc[j][0] = bia[j][0]; acc[j][1] = bia[j][1]; acc[j][2] = bia[j][0]; acc[j][3] = bia[j][1];
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+#define RTOD_MMA(A)                                                                                          \
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, " \
+                 "{%0,%1,%2,%3};"                                                                            \
+                 : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])                        \
+                 : "r"(A[s2][0]), "r"(A[s2][1]), "r"(A[s2][2]), "r"(A[s2][3]), "r"(bfr[j][s2][0]), "r"(bfr[j][s2][1]))
+                    RTOD_MMA(alo);
+                    RTOD_MMA(ahi);
+#undef RTOD_MMA
+                }
+            }
+            const long long row_pix = ((long long)b * p.H + y) * p.W;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int x = x_first + px0 + g + 8 * rr;
+                if (x >= p.W) continue;
+                __nv_bfloat16* dst = obase + (row_pix + x) * p.out.pitch + 2 * t;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    float v0 = acc[j][2 * rr], v1 = acc[j][2 * rr + 1];
+                    if (p.leaky) {
+                        v0 = fmaxf(v0, 0.1f * v0);
+                        v1 = fmaxf(v1, 0.1f * v1);
+                    }
+                    *reinterpret_cast<uint32_t*>(dst + 8 * j) = pack_bf16x2(v0, v1);
+                }
+            }
+        }
+        __syncthreads();                              // every warp is done with stage s
+    }
+}
+
+}  // namespace
+
+// returns RTOD_ERR_UNSUPPORTED (without touching the error text semantics) when the shape is not covered
+int launch_stem_tma(const float* x, int B, int H, int W, const float* w, const float* bias, int Cout, int leaky,
+                    Act out, cudaStream_t stream) {
+    static EncodeTiledFn encode_tiled = nullptr;
+    if (!encode_tiled) {
+        const int rc = driver_fn("cuTensorMapEncodeTiled", reinterpret_cast<void**>(&encode_tiled));
+        if (rc) return rc;
+    }
+    StemParams p{};
+    int n_seg = (W + 239) / 240;
+    if (n_seg < 2) n_seg = 2;                                  // the box (SW + 4 columns) must not exceed the image width
+    p.SW = ((W + n_seg - 1) / n_seg + 15) / 16 * 16;            // strip width, multiple of 16, <= 240
+    p.box_w = p.SW + 8;                                        // 4 columns left (alignment), 1 + 3 right
+    if (p.box_w > W) return fail(RTOD_ERR_UNSUPPORTED, "stem_tma: image width %d too small", W);
+    p.strips_per_row = (W + p.SW - 1) / p.SW;
+    p.total_strips = B * H * p.strips_per_row;
+    p.tiles_per_strip = p.SW / 16;
+    p.dbg = getenv("RTOD_STEM_DBG") ? atoi(getenv("RTOD_STEM_DBG")) : 0;
+    p.w = w; p.bias = bias; p.out = out; p.B = B; p.H = H; p.W = W; p.leaky = leaky;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)3 * B};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)p.box_w, 3, 3};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode_tiled(&p.tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box,
+                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (stem image) failed: %d", (int)r);
+    int warps = p.tiles_per_strip;
+    if (warps > 16) warps = 16;
+    if (warps < 2) warps = 2;
+    const size_t smem = (size_t)kStemStages * (((size_t)9 * p.box_w * 4 + 127) & ~(size_t)127) + kStemStages * 8 + 16 + 256;
+    const int per_sm = warps >= 8 ? 1 : 2;                       // register-bound: ~16-20 warps per SM
+    int grid = kNumSMs * per_sm;
+    if (grid > p.total_strips) grid = p.total_strips;
+    if (Cout == 32) stem_tma_kernel<4><<<grid, warps * 32, smem, stream>>>(p);
+    else if (Cout == 16) stem_tma_kernel<2><<<grid, warps * 32, smem, stream>>>(p);
+    else stem_tma_kernel<8><<<grid, warps * 32, smem, stream>>>(p);
+    RTOD_LAUNCH_OK("stem_tma_kernel");
+    return RTOD_OK;
+}
+
+}  // namespace rtod
