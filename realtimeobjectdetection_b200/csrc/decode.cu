@@ -83,10 +83,26 @@ yolo_decode_heads_kernel(DecodeHeads heads, int B, int N, int L, int train, int 
         const float* src = heads.raw[h] + ((long long)b * G * G + cell) * heads.pitch[h];
         float* dst = pred + ((long long)b * N + heads.row_base[h] + (long long)cell * A) * L;
         const int n = A * L;
+        int a = lane / L, attr = lane - a * L;               // (anchor, attribute) advance by additions
+        const int step_a = 32 / L, step_attr = 32 - step_a * L;
         for (int e = lane; e < n; e += 32) {
-            const int a = e / L, attr = e - a * L;
-            dst[e] = decode_value(__ldg(src + e), attr, cx, cy, heads.anchor_w[h][a], heads.anchor_h[h][a],
-                                  stride, train);
+            const float v = __ldg(src + e);
+            float r;
+            if (attr >= 4) {
+                r = sigmoid_f32(v);
+            } else if (attr < 2) {
+                r = sigmoid_f32(v);
+                if (!train) r = __fmul_rn(__fadd_rn(r, (float)(attr == 0 ? cx : cy)), stride);
+            } else {
+                r = train ? v : __fmul_rn(__fmul_rn(expf(v), attr == 2 ? heads.anchor_w[h][a] : heads.anchor_h[h][a]), stride);
+            }
+            dst[e] = r;
+            a += step_a;
+            attr += step_attr;
+            if (attr >= L) {
+                attr -= L;
+                ++a;
+            }
         }
     }
 }

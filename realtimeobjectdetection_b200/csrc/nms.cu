@@ -24,8 +24,10 @@ constexpr unsigned long long kDeadKey = ~0ull;
 constexpr int kScanThreads = 256;
 constexpr int kScanMaxRows = 64;
 constexpr int kScanStageBytes = 24576;
+constexpr int kScanStages = 3;
 constexpr int kImageThreads = 1024;
-constexpr int kSortSmemCap = 16384;          // keys sortable in shared memory per image
+constexpr int kSortSmemCap = 16384;          // keys sortable in shared memory per image (heavy pass)
+constexpr int kLightCap = 4096;              // ... in the light pass
 
 // ---- exact-reference arithmetic -----------------------------------------------------------
 __device__ __forceinline__ float nan_max(float a, float b) {   // torch.max propagates NaN
@@ -113,19 +115,19 @@ nms_scan_kernel(const float* __restrict__ pred, long long total_rows, int N, int
                 float conf, int P, int rows_per_chunk, int use_bulk, int* __restrict__ cand_count,
                 unsigned long long* __restrict__ keys, int* __restrict__ err_flag) {
     extern __shared__ __align__(128) unsigned char scan_smem[];
-    __shared__ __align__(8) unsigned long long bars[2];
+    __shared__ __align__(8) unsigned long long bars[kScanStages];
     __shared__ unsigned keep_words[2];
     __shared__ int slot_base[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int stage_floats = rows_per_chunk * L;
-    float* stage_buf[2] = {reinterpret_cast<float*>(scan_smem),
-                           reinterpret_cast<float*>(scan_smem) + ((stage_floats + 31) / 32) * 32};
+    float* stage_buf[kScanStages];
+    for (int s = 0; s < kScanStages; ++s)
+        stage_buf[s] = reinterpret_cast<float*>(scan_smem) + (size_t)s * (((stage_floats + 31) / 32) * 32);
     const long long n_chunks = (total_rows + rows_per_chunk - 1) / rows_per_chunk;
 
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        for (int s = 0; s < kScanStages; ++s) mbar_init(&bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -151,22 +153,26 @@ nms_scan_kernel(const float* __restrict__ pred, long long total_rows, int N, int
         }
     };
 
-    uint32_t phase[2] = {0u, 0u};
+    // chunk `it` of this CTA lives in stage it % kScanStages; two chunks are in flight while one is processed
+    uint32_t phase_bits = 0u;
     long long c = blockIdx.x;
-    if (c < n_chunks) prefetch(c, 0);
+    for (int pre = 0; pre < kScanStages - 1; ++pre)
+        if (c + (long long)pre * gridDim.x < n_chunks) prefetch(c + (long long)pre * gridDim.x, pre);
     for (int it = 0; c < n_chunks; ++it, c += gridDim.x) {
-        const int s = it & 1;
-        const long long next = c + gridDim.x;
-        if (next < n_chunks) prefetch(next, s ^ 1);
+        const int s = it % kScanStages;
+        const long long ahead = c + (long long)(kScanStages - 1) * gridDim.x;
+        if (ahead < n_chunks) prefetch(ahead, (it + kScanStages - 1) % kScanStages);   // freed by the sync below
         if (chunk_is_bulk(c)) {
-            const unsigned long long t0 = global_timer_ns();
-            while (!mbar_try_wait(&bars[s], phase[s])) {
-                if (global_timer_ns() - t0 > 2000000000ull) {     // 2 s: report, do not hang
-                    atomicExch(err_flag, 1);
-                    break;
+            if (tid == 0) {                               // one waiter; the barrier below publishes the data
+                const unsigned long long t0 = global_timer_ns();
+                while (!mbar_try_wait(&bars[s], (phase_bits >> s) & 1u)) {
+                    if (global_timer_ns() - t0 > 2000000000ull) {     // 2 s: report, do not hang
+                        atomicExch(err_flag, 1);
+                        break;
+                    }
                 }
             }
-            phase[s] ^= 1u;
+            phase_bits ^= 1u << s;
         }
         __syncthreads();
 
@@ -276,22 +282,29 @@ __device__ __forceinline__ int upper_bound_class(const unsigned long long* keys,
     return lo;
 }
 
+// Launched twice per call: a light configuration (512 threads, 4096 keys in shared memory, four CTAs per
+// SM) that takes the images with n_lo < n <= n_hi candidates -- the normal case -- and a heavy one
+// (1024 threads, 16384 keys, one CTA per SM; > 16384 candidates sort in global memory) for dense
+// images; CTAs whose image is out of their range exit at once.
 __global__ void __launch_bounds__(kImageThreads)
 nms_image_kernel(const float* __restrict__ pred, int N, int L, float conf, float nms_thr, int P,
                  const int* __restrict__ cand_count, unsigned long long* __restrict__ keys_g,
                  uint32_t* __restrict__ klist_g, uint32_t* __restrict__ kbits_g,
-                 uint32_t* __restrict__ kept_pair, int* __restrict__ kept_count, int smem_cap) {
+                 uint32_t* __restrict__ kept_pair, int* __restrict__ kept_count, int smem_cap, int n_lo,
+                 int n_hi) {
     extern __shared__ __align__(16) unsigned char image_smem[];
     __shared__ int s_live, s_cursor, s_total;
     __shared__ int s_warp_sums[kImageThreads / 32];
 
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = blockDim.x;
     int n = cand_count[img];
     if (n > N) n = N;
     if (n <= 0) {
-        if (tid == 0) kept_count[img] = 0;
+        if (n_lo < 0 && tid == 0) kept_count[img] = 0;     // the light pass owns the empty images
         return;
     }
+    if (n <= n_lo || n > n_hi) return;                       // the other pass handles this image
     int np = 32;
     while (np < n) np <<= 1;
 
@@ -302,14 +315,14 @@ nms_image_kernel(const float* __restrict__ pred, int N, int L, float conf, float
         keys = reinterpret_cast<unsigned long long*>(image_smem);
         klist = reinterpret_cast<uint32_t*>(image_smem + (size_t)smem_cap * 8);
         kbits = reinterpret_cast<uint32_t*>(image_smem + (size_t)smem_cap * 12);
-        for (int i = tid; i < np; i += kImageThreads) keys[i] = i < n ? src[i] : kDeadKey;
+        for (int i = tid; i < np; i += nthreads) keys[i] = i < n ? src[i] : kDeadKey;
     } else {
         keys = src;
         klist = klist_g + (long long)img * P;
         kbits = kbits_g + (long long)img * (P / 32);
-        for (int i = n + tid; i < np; i += kImageThreads) keys[i] = kDeadKey;
+        for (int i = n + tid; i < np; i += nthreads) keys[i] = kDeadKey;
     }
-    for (int i = tid; i < np / 32; i += kImageThreads) kbits[i] = 0u;
+    for (int i = tid; i < np / 32; i += nthreads) kbits[i] = 0u;
     if (tid == 0) {
         s_live = 0;
         s_cursor = 0;
@@ -319,7 +332,7 @@ nms_image_kernel(const float* __restrict__ pred, int N, int L, float conf, float
     // ---- bitonic sort, ascending: class up, objectness down, row index up --------------------
     for (int k = 2; k <= np; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (np >> 1); t += kImageThreads) {
+            for (int t = tid; t < (np >> 1); t += nthreads) {
                 const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 const int l = i | j;
                 const unsigned long long a = keys[i], b = keys[l];
@@ -332,7 +345,7 @@ nms_image_kernel(const float* __restrict__ pred, int N, int L, float conf, float
             __syncthreads();
         }
     }
-    for (int i = tid; i < np; i += kImageThreads)
+    for (int i = tid; i < np; i += nthreads)
         if (keys[i] != kDeadKey && (i + 1 == np || keys[i + 1] == kDeadKey)) s_live = i + 1;
     __syncthreads();
     const int n_live = s_live;
@@ -412,7 +425,7 @@ nms_image_kernel(const float* __restrict__ pred, int N, int L, float conf, float
     // ---- ordered compaction of kept positions -> (row | class << 20) -----------------------------
     int running = 0;
     const int n_words = np / 32;
-    for (int w0 = 0; w0 < n_words; w0 += kImageThreads) {
+    for (int w0 = 0; w0 < n_words; w0 += nthreads) {
         const int w = w0 + tid;
         const uint32_t word = w < n_words ? kbits[w] : 0u;
         const int cnt = __popc(word);
@@ -425,7 +438,7 @@ nms_image_kernel(const float* __restrict__ pred, int N, int L, float conf, float
         if (lane == 31) s_warp_sums[warp] = incl;
         __syncthreads();
         if (warp == 0) {
-            int v = s_warp_sums[lane];
+            int v = lane < (nthreads >> 5) ? s_warp_sums[lane] : 0;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
                 const int u = __shfl_up_sync(0xffffffffu, v, off);
@@ -605,11 +618,11 @@ extern "C" int rtod_write_results(const float* pred, int B, int N, int C, float 
     const int use_bulk = ((reinterpret_cast<uintptr_t>(pred) & 15u) == 0) &&
                          (((long long)rows_per_chunk * L) % 4 == 0);
     const size_t stage_bytes = (size_t)(((rows_per_chunk * L + 31) / 32) * 32) * 4;
-    const size_t scan_smem = 2 * stage_bytes;
+    const size_t scan_smem = kScanStages * stage_bytes;
     static bool scan_attr_set = false;
     if (!scan_attr_set) {
         RTOD_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          2 * (kScanStageBytes + 128)));
+                                          kScanStages * (kScanStageBytes + 128)));
         scan_attr_set = true;
     }
     const long long total_rows = (long long)B * N;
@@ -625,18 +638,26 @@ extern "C" int rtod_write_results(const float* pred, int B, int N, int C, float 
     RTOD_LAUNCH_OK("nms_scan_kernel");
 
     // ---- per-image sort + suppression ---------------------------------------------------
-    const int smem_cap = lay.P < kSortSmemCap ? lay.P : kSortSmemCap;
-    const size_t image_smem = (size_t)smem_cap * 12 + smem_cap / 8;
     static bool image_attr_set = false;
     if (!image_attr_set) {
         RTOD_CUDA_OK(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           kSortSmemCap * 12 + kSortSmemCap / 8));
         image_attr_set = true;
     }
-    nms_image_kernel<<<B, kImageThreads, image_smem, stream>>>(pred, N, L, confidence, nms_conf, lay.P,
-                                                               cand_count, keys, klist, kbits, pair,
-                                                               kept_count, smem_cap);
-    RTOD_LAUNCH_OK("nms_image_kernel");
+    {   // light pass: images with at most kLightCap candidates (and the empty ones)
+        const int cap = lay.P < kLightCap ? lay.P : kLightCap;
+        nms_image_kernel<<<B, 512, (size_t)cap * 12 + cap / 8, stream>>>(pred, N, L, confidence, nms_conf, lay.P,
+                                                                        cand_count, keys, klist, kbits, pair,
+                                                                        kept_count, cap, -1, cap);
+        RTOD_LAUNCH_OK("nms_image_kernel (light)");
+        if (lay.P > kLightCap) {   // heavy pass: dense images
+            const int hcap = lay.P < kSortSmemCap ? lay.P : kSortSmemCap;
+            nms_image_kernel<<<B, kImageThreads, (size_t)hcap * 12 + hcap / 8, stream>>>(
+                pred, N, L, confidence, nms_conf, lay.P, cand_count, keys, klist, kbits, pair, kept_count, hcap,
+                kLightCap, 0x7fffffff);
+            RTOD_LAUNCH_OK("nms_image_kernel (heavy)");
+        }
+    }
 
     // ---- emit ---------------------------------------------------------------------------------
     nms_emit_kernel<<<B, 256, 0, stream>>>(pred, B, N, L, confidence, pair, kept_count, out_rows, cap,
