@@ -61,7 +61,7 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 
 // logistic function with full-precision exp and IEEE division (reference: torch.sigmoid, fp32)
 __device__ __forceinline__ float sigmoid_f32(float v) {
-    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+    return __frcp_rn(__fadd_rn(1.0f, expf(-v)));          // correctly rounded reciprocal == 1.0f / x
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

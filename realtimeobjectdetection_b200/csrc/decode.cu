@@ -46,13 +46,33 @@ yolo_decode_nchw_kernel(const float* __restrict__ head, int G, int A, int L, flo
         tile[ch][cl] = cl < n_cell ? src[(long long)ch * GG + cl] : 0.0f;
     }
     __syncthreads();
-    for (int o = threadIdx.x; o < n_cell * n_ch; o += 256) {
-        const int cl = o / n_ch, chl = o % n_ch;
-        const int ch = ch0 + chl, cell = cell0 + cl;
-        const int a = ch / L, attr = ch % L;
-        const float v = decode_value(tile[chl][cl], attr, cell % G, cell / G, anchors.w[a],
-                                     anchors.h[a], stride, train);
-        out[((long long)b * GG + cell) * Ch + ch] = v;
+    // one warp per cell: its channels are contiguous in the output, (anchor, attribute) advance by additions
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int step_a = 32 / L, step_attr = 32 - step_a * L;
+    for (int cl = warp; cl < n_cell; cl += 8) {
+        const int cell = cell0 + cl;
+        const int cx = cell % G, cy = cell / G;
+        int a = (ch0 + lane) / L, attr = (ch0 + lane) - a * L;
+        float* dst = out + ((long long)b * GG + cell) * Ch + ch0;
+        for (int chl = lane; chl < n_ch; chl += 32) {
+            const float v = tile[chl][cl];
+            float r;
+            if (attr >= 4) {
+                r = sigmoid_f32(v);
+            } else if (attr < 2) {
+                r = sigmoid_f32(v);
+                if (!train) r = __fmul_rn(__fadd_rn(r, (float)(attr == 0 ? cx : cy)), stride);
+            } else {
+                r = train ? v : __fmul_rn(__fmul_rn(expf(v), attr == 2 ? anchors.w[a] : anchors.h[a]), stride);
+            }
+            dst[chl] = r;
+            a += step_a;
+            attr += step_attr;
+            if (attr >= L) {
+                attr -= L;
+                ++a;
+            }
+        }
     }
 }
 

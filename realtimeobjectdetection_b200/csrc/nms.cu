@@ -16,6 +16,8 @@
 // separate rounding, so fused multiply-add contraction must not happen here.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace rtod {
 
 namespace {
@@ -153,17 +155,18 @@ nms_scan_kernel(const float* __restrict__ pred, long long total_rows, int N, int
         }
     };
 
-    // chunk `it` of this CTA lives in stage it % kScanStages; two chunks are in flight while one is processed
+    // chunk `it` of this CTA lives in stage it % kScanStages; two chunks are in flight while one is
+    // processed.  Two CTA barriers per chunk: (A) the chunk has landed and everybody is done with the
+    // previous one, (B) warp 0 has published the keep mask and the reserved slots.
     uint32_t phase_bits = 0u;
     long long c = blockIdx.x;
     for (int pre = 0; pre < kScanStages - 1; ++pre)
         if (c + (long long)pre * gridDim.x < n_chunks) prefetch(c + (long long)pre * gridDim.x, pre);
+    const bool grouped = N >= rows_per_chunk;                 // a chunk touches at most two images
     for (int it = 0; c < n_chunks; ++it, c += gridDim.x) {
         const int s = it % kScanStages;
-        const long long ahead = c + (long long)(kScanStages - 1) * gridDim.x;
-        if (ahead < n_chunks) prefetch(ahead, (it + kScanStages - 1) % kScanStages);   // freed by the sync below
         if (chunk_is_bulk(c)) {
-            if (tid == 0) {                               // one waiter; the barrier below publishes the data
+            if (tid == 0) {                               // one waiter; barrier (A) publishes the data
                 const unsigned long long t0 = global_timer_ns();
                 while (!mbar_try_wait(&bars[s], (phase_bits >> s) & 1u)) {
                     if (global_timer_ns() - t0 > 2000000000ull) {     // 2 s: report, do not hang
@@ -174,43 +177,51 @@ nms_scan_kernel(const float* __restrict__ pred, long long total_rows, int N, int
             }
             phase_bits ^= 1u << s;
         }
-        __syncthreads();
+        __syncthreads();                                  // (A)
+        const long long ahead = c + (long long)(kScanStages - 1) * gridDim.x;
+        if (ahead < n_chunks) prefetch(ahead, (it + kScanStages - 1) % kScanStages);   // stage of chunk it-1
+        if (use_bulk & 4) continue;                           // timing experiment only: stream, do not process
 
         const float* buf = stage_buf[s];
         const long long first = c * rows_per_chunk;
-        int rows = (int)((total_rows - first) < rows_per_chunk ? (total_rows - first) : rows_per_chunk);
+        const int rows = (int)((total_rows - first) < rows_per_chunk ? (total_rows - first) : rows_per_chunk);
+        const long long img_a = first / N;
+        const int split = (int)((img_a + 1) * (long long)N - first);   // rows of image a in this chunk
 
-        // (a) objectness threshold: strict '>' in fp32, then "masked objectness != 0"
-        if (tid < 64) {
-            bool keep = false;
-            if (tid < rows) {
-                const float obj = buf[tid * L + 4];
-                const float m = obj > conf ? 1.0f : 0.0f;
-                keep = __fmul_rn(obj, m) != 0.0f;
+        // (a) warp 0: objectness threshold (strict '>' in fp32, then "masked objectness != 0") for all
+        //     rows (two per lane), and one atomicAdd per image touched to reserve contiguous slots
+        if (warp == 0) {
+            bool k0 = false, k1 = false;
+            if (lane < rows) {
+                const float obj = buf[lane * L + 4];
+                k0 = __fmul_rn(obj, obj > conf ? 1.0f : 0.0f) != 0.0f;
             }
-            const unsigned word = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) keep_words[warp] = word;
+            if (lane + 32 < rows) {
+                const float obj = buf[(lane + 32) * L + 4];
+                k1 = __fmul_rn(obj, obj > conf ? 1.0f : 0.0f) != 0.0f;
+            }
+            const unsigned w0 = __ballot_sync(0xffffffffu, k0), w1 = __ballot_sync(0xffffffffu, k1);
+            if (lane == 0) {
+                keep_words[0] = w0;
+                keep_words[1] = w1;
+                if (grouped) {
+                    const unsigned long long km = (unsigned long long)w0 | ((unsigned long long)w1 << 32);
+                    const unsigned long long lo_mask = split >= 64 ? ~0ull : ((1ull << split) - 1ull);
+                    const int cnt_a = __popcll(km & lo_mask), cnt_b = __popcll(km & ~lo_mask);
+                    slot_base[0] = cnt_a ? atomicAdd(&cand_count[img_a], cnt_a) : 0;
+                    slot_base[1] = cnt_b ? atomicAdd(&cand_count[img_a + 1], cnt_b) : 0;
+                }
+            }
         }
-        __syncthreads();
+        __syncthreads();                                  // (B)
         const unsigned long long kmask =
             (unsigned long long)keep_words[0] | ((unsigned long long)keep_words[1] << 32);
 
-        // (b) reserve contiguous slots per image touched by the chunk (at most two when
-        //     N >= rows_per_chunk; otherwise every row reserves its own slot)
-        const bool grouped = N >= rows_per_chunk;
-        const long long img_a = first / N;
-        const int split = (int)((img_a + 1) * (long long)N - first);   // rows of image a in chunk
-        if (grouped && tid == 0) {
-            const unsigned long long lo_mask = split >= 64 ? ~0ull : ((1ull << split) - 1ull);
-            const int cnt_a = __popcll(kmask & lo_mask), cnt_b = __popcll(kmask & ~lo_mask);
-            slot_base[0] = cnt_a ? atomicAdd(&cand_count[img_a], cnt_a) : 0;
-            slot_base[1] = cnt_b ? atomicAdd(&cand_count[img_a + 1], cnt_b) : 0;
-        }
-        __syncthreads();
-
-        // (c) one warp per surviving row: first-max class, key, append
-        for (int r = warp; r < rows; r += kScanThreads / 32) {
-            if (!((kmask >> r) & 1ull)) continue;
+        // (b) the i-th surviving row goes to warp i % 8: first-max class, key, append
+        int ordinal = 0;
+        for (unsigned long long rest = kmask; rest; rest &= rest - 1, ++ordinal) {
+            if ((ordinal & 7) != warp) continue;
+            const int r = __ffsll((long long)rest) - 1;
             const float* row = buf + r * L;
             const float obj = row[4];
             const float m = obj > conf ? 1.0f : 0.0f;
@@ -245,12 +256,8 @@ nms_scan_kernel(const float* __restrict__ pred, long long total_rows, int N, int
                 const int row_in_img = (int)(grow - img * N);
                 int slot;
                 if (grouped) {
-                    const unsigned long long below = kmask & ((1ull << r) - 1ull);
-                    if (r < split) slot = slot_base[0] + __popcll(below);
-                    else {
-                        const unsigned long long lo_mask = (1ull << split) - 1ull;
-                        slot = slot_base[1] + __popcll(below & ~lo_mask);
-                    }
+                    if (r < split) slot = slot_base[0] + ordinal;
+                    else slot = slot_base[1] + ordinal - __popcll(kmask & ((1ull << split) - 1ull));
                 } else {
                     slot = atomicAdd(&cand_count[img], 1);
                 }
@@ -264,7 +271,6 @@ nms_scan_kernel(const float* __restrict__ pred, long long total_rows, int N, int
                 keys[img * (long long)P + slot] = key;
             }
         }
-        __syncthreads();
     }
 }
 
@@ -615,8 +621,9 @@ extern "C" int rtod_write_results(const float* pred, int B, int N, int C, float 
     if (rows_per_chunk > kScanMaxRows) rows_per_chunk = kScanMaxRows;
     if (rows_per_chunk >= 4) rows_per_chunk &= ~3;
     if (rows_per_chunk < 1) rows_per_chunk = 1;
-    const int use_bulk = ((reinterpret_cast<uintptr_t>(pred) & 15u) == 0) &&
+    int use_bulk = ((reinterpret_cast<uintptr_t>(pred) & 15u) == 0) &&
                          (((long long)rows_per_chunk * L) % 4 == 0);
+    if (const char* e = getenv("RTOD_NMS_DBG")) use_bulk |= atoi(e) << 1;
     const size_t stage_bytes = (size_t)(((rows_per_chunk * L + 31) / 32) * 32) * 4;
     const size_t scan_smem = kScanStages * stage_bytes;
     static bool scan_attr_set = false;

@@ -203,6 +203,51 @@ def stage_layers():
         print("  decode %8.1f us" % (acc[n] * 1e3))
 
 
+def stage_nmsbench():
+    """BASELINE configs[3]: write_results on [256, 10647, 85] at 1/10/50 % density, C-ABI call only
+    (CUDA events), plus the decode microbench on [256, 255, G, G] heads."""
+    import ctypes
+    lib = _lib.load()
+    B, N, C = 256, 10647, 80
+    nbytes = lib.rtod_write_results_workspace_bytes(B, N, C)
+    ws = torch.empty(nbytes + 256, dtype=torch.uint8, device="cuda")
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    rows = torch.empty(B * N, 8, device="cuda")
+    count = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for dens, clustered in ((0.01, False), (0.01, True), (0.10, True), (0.50, True), (0.50, False)):
+        pred = torch.from_numpy(synth_pred(0, B, N, C, dens, clustered)).cuda()
+        for _ in range(3):
+            _lib.check(lib.rtod_write_results(pred.data_ptr(), B, N, C, 0.5, 0.4, rows.data_ptr(), B * N,
+                                              count.data_ptr(), ws_ptr, nbytes, st))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            _lib.check(lib.rtod_write_results(pred.data_ptr(), B, N, C, 0.5, 0.4, rows.data_ptr(), B * N,
+                                              count.data_ptr(), ws_ptr, nbytes, st))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        print("write_results [256,10647,85] density %.2f clustered %d: %.1f us -> %.0f GB/s (%.2f of 6552.6), %d detections"
+              % (dens, clustered, ms * 1e3, pred.numel() * 4 / ms / 1e6, pred.numel() * 4 / ms / 1e6 / 6552.6, int(count.item())))
+        del pred
+    anchors = (ctypes.c_float * 6)(116, 90, 156, 198, 373, 326)
+    for G in (13, 26, 52):
+        head = torch.randn(B, 255, G, G, device="cuda")
+        out = torch.empty(B, G * G * 3, 85, device="cuda")
+        for _ in range(3):
+            _lib.check(lib.rtod_yolo_decode(head.data_ptr(), B, G, 3, 80, 416, anchors, 0, out.data_ptr(), st))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            _lib.check(lib.rtod_yolo_decode(head.data_ptr(), B, G, 3, 80, 416, anchors, 0, out.data_ptr(), st))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        print("yolo_decode [256,255,%d,%d]: %.1f us -> %.0f GB/s (%.2f of 6552.6)" %
+              (G, G, ms * 1e3, head.numel() * 8 / ms / 1e6, head.numel() * 8 / ms / 1e6 / 6552.6))
+
+
 if __name__ == "__main__":
     stage = sys.argv[1]
     torch.backends.cudnn.allow_tf32 = False
