@@ -356,21 +356,34 @@ nms_image_kernel(const float* __restrict__ pred, int N, int L, float conf, float
     __syncthreads();
     const int n_live = s_live;
 
-    // ---- greedy suppression: warps claim class segments -----------------------------------------
+    // ---- greedy suppression: class c belongs to warp c % nwarps.  Each lane finds the segment of one of
+    //      its warp's classes by binary search in the sorted keys (no claiming, no contention), then the
+    //      warp walks through the non-empty segments one after the other.
     const float* img_pred = pred + (long long)img * N * L;
-    while (true) {
-        int seg_lo = 0, seg_hi = 0;
-        if (lane == 0) {
-            while (true) {
-                seg_lo = *(volatile int*)&s_cursor;
-                if (seg_lo >= n_live) break;
-                seg_hi = upper_bound_class(keys, seg_lo, n_live, keys[seg_lo] >> 52);
-                if (atomicCAS(&s_cursor, seg_lo, seg_hi) == seg_lo) break;
-            }
+    const int nwarps = nthreads >> 5;
+    const int n_classes = L - 5;
+    auto lower_bound_class = [&](unsigned long long cls) {     // first position with class field >= cls
+        int lo = 0, hi = n_live;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((keys[mid] >> 52) < cls) lo = mid + 1;
+            else hi = mid;
         }
-        seg_lo = __shfl_sync(0xffffffffu, seg_lo, 0);
-        seg_hi = __shfl_sync(0xffffffffu, seg_hi, 0);
-        if (seg_lo >= n_live) break;
+        return lo;
+    };
+    for (int cbase = warp; cbase < n_classes; cbase += nwarps * 32) {
+        const int my_cls = cbase + lane * nwarps;
+        int my_lo = 0, my_hi = 0;
+        if (my_cls < n_classes) {
+            my_lo = lower_bound_class((unsigned long long)my_cls);
+            my_hi = lower_bound_class((unsigned long long)my_cls + 1ull);
+        }
+        unsigned nonempty = __ballot_sync(0xffffffffu, my_hi > my_lo);
+      while (nonempty) {
+        const int src_lane = __ffs(nonempty) - 1;
+        nonempty &= nonempty - 1;
+        const int seg_lo = __shfl_sync(0xffffffffu, my_lo, src_lane);
+        const int seg_hi = __shfl_sync(0xffffffffu, my_hi, src_lane);
 
         int kept_in_seg = 0;
         for (int t0 = seg_lo; t0 < seg_hi; t0 += 32) {
@@ -425,6 +438,7 @@ nms_image_kernel(const float* __restrict__ pred, int N, int L, float conf, float
             }
             __syncwarp();
         }
+      }
     }
     __syncthreads();
 
