@@ -300,25 +300,57 @@ def run_b200(args):
     achieved = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": achieved,
                 "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+                "frac": achieved / peaks["tflops_sustained"],
+                # dram__bytes_read + dram__bytes_write of one captured launch (13x13 3x3 512->1024 layer at B=64,
+                # profiles/r1c_conv_tc_ncu.txt); its algorithmic bytes (in + weights + out, bf16) are 42.6 MB
+                "traffic": 43.85e6 if (args.cfg == "yolov3" and B == 64) else None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s): kernel timed inside a long step"
                                % peaks["source"],
                 "launches_per_step": n_tc, "flops_per_step": tc_flops / reps,
                 "avg_launch_ms": tc_ms / reps / max(n_tc, 1), "share_of_forward": tc_ms / reps / fwd_ms}
 
-    # NMS stage (HBM bound): device time of rtod_write_results on this step's prediction tensor
+    # NMS stage (HBM bound): device time of the rtod_write_results C-ABI call (scan + image x2 + emit
+    # kernels) on this step's prediction tensor, and on the BASELINE configs[3] microbench tensor
+    def time_write_results(pred_t, iters=10):
+        Bq, Nq, Lq = pred_t.shape
+        nbytes = lib.rtod_write_results_workspace_bytes(Bq, Nq, Lq - 5)
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        rows_t = torch.empty(Bq * Nq, 8, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        for i in range(iters + 3):
+            if i == 3:
+                torch.cuda.synchronize()
+                e0.record()
+            _lib.check(lib.rtod_write_results(pred_t.data_ptr(), Bq, Nq, Lq - 5, CONF, NMS, rows_t.data_ptr(), Bq * Nq,
+                                              cnt.data_ptr(), ws_ptr, nbytes, st))
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters, int(cnt.item())
+
     pred = model(frames[0])
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(5):
-        write_results(pred, CLASSES, CONF, NMS)
-    e1.record()
-    torch.cuda.synchronize()
-    nms_ms = e0.elapsed_time(e1) / 5
+    nms_ms, _ = time_write_results(pred)
     nms_bytes = pred.numel() * 4
-    roofline_nms = {"bound": "hbm", "kernel": "nms_scan+nms_image+nms_emit (write_results call)",
+    roofline_nms = {"bound": "hbm", "kernel": "rtod_write_results: nms_scan + nms_image(light, heavy) + nms_emit",
                     "achieved": nms_bytes / nms_ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": nms_bytes / nms_ms / 1e6 / peaks["hbm_gbs"], "traffic": None, "ms": nms_ms}
+                    "frac": nms_bytes / nms_ms / 1e6 / peaks["hbm_gbs"], "traffic": None, "ms": nms_ms,
+                    "tensor": list(pred.shape)}
+    microbench = None
+    if rank == 0 and not args.no_latency:
+        # BASELINE configs[3]: [256, 10647, 85], 1 % of the rows above the threshold, generated on device
+        g2 = torch.Generator(device=dev)
+        g2.manual_seed(7)
+        mb = torch.rand(256, 10647, 85, device=dev, generator=g2)
+        mb[..., 0:2] *= RESO
+        mb[..., 2:4] = torch.exp(mb[..., 2:4] * 3 + 2)
+        hot = torch.rand(256, 10647, device=dev, generator=g2) < 0.01
+        mb[..., 4] = torch.where(hot, 0.5 + 0.4995 * mb[..., 4], 0.4995 * mb[..., 4])
+        mb_ms, mb_det = time_write_results(mb)
+        microbench = {"what": "write_results on [256,10647,85] fp32, 1% of rows above conf 0.5 (uniform boxes)",
+                      "ms": mb_ms, "GB/s": mb.numel() * 4 / mb_ms / 1e6,
+                      "frac_of_hbm_peak": mb.numel() * 4 / mb_ms / 1e6 / peaks["hbm_gbs"], "detections": mb_det}
+        del mb, hot
 
     # ---- p50 batch-1 latency (BASELINE configs[1]) ---------------------------------------------------
     latency = None
@@ -360,7 +392,7 @@ def run_b200(args):
                        "detections_per_step": n_det / max(K, 1), "cuda_graph": bool(model.use_cuda_graph)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K,
             "gpu_launches_per_step": launches_per_step,
-            "roofline": roofline, "roofline_nms": roofline_nms,
+            "roofline": roofline, "roofline_nms": roofline_nms, "nms_microbench": microbench,
             "forward_tflops": FRAME_GFLOP * world * B / (ms_total / K) if args.cfg == "yolov3" else None,
             "latency_batch1": latency, "cpu_baseline": cpu, "layers": per_layer,
         }
