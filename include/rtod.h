@@ -152,6 +152,12 @@ int rtod_confidence_mask(const float* pred, long long rows, int attrs, float con
 int rtod_bbox_iou(const float* box1, int n1, int stride1, const float* box2, int n2, int stride2,
                   float* out, void* stream);
 
+/* ---- measurement aid (bench.py "clocks"; no reference counterpart) ------------------------
+ * One thread samples the SM clock it runs on: `samples` windows of `interval_us` microseconds,
+ * out_mhz[i] = SM cycles / wall time of window i.  Launch it on a side stream next to the work
+ * being measured; it ends by itself after samples * interval_us. */
+int rtod_sm_clock_probe(float* out_mhz, int samples, int interval_us, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,7 @@ _PROTOTYPES = {
     "rtod_write_results": (_i, [_vp, _i, _i, _i, _f, _f, _vp, _i, _vp, _vp, _sz, _vp]),
     "rtod_confidence_mask": (_i, [_vp, ctypes.c_longlong, _i, _f, _vp, _vp]),
     "rtod_bbox_iou": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "rtod_sm_clock_probe": (_i, [_vp, _i, _i, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(sorted(_PROTOTYPES))
 

@@ -1,0 +1,152 @@
+// conv_epilogue.cuh -- epilogue shared by the tcgen05 convolution kernels (conv_tc.cu, conv_pair.cu):
+// accumulator (TMEM) -> + folded bias -> leaky 0.1 -> + shortcut operand -> bf16 (fp32 for head logits)
+// -> swizzled shared memory -> TMA store (src/darknet.py:292-295 BN/LeakyReLU, :263-268 shortcut).
+//
+// Every epilogue warp is its own pipeline -- no CTA-level barrier: warp w may only read TMEM lanes
+// [32*(w%4), +32), i.e. 32 rows of the 128-row tile; it owns `stage_bufs` staging slices of 32 rows x
+// 128 B, stores each finished slice with its own TMA store (box {ecols, 32 rows}; rows >= M and
+// channels >= Cout are clipped by the descriptor) and, for shortcut layers, TMA-loads the operand of
+// its NEXT chunk into the slice it is about to reuse (the sum is formed in place).  With 8 epilogue
+// warps the two warps that share a TMEM lane quarter split the tile's column chunks (even / odd).
+#pragma once
+#include "conv_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace rtod {
+
+constexpr uint32_t kEpiSlice = 4096;            // one warp's staging slice: 32 rows x 128 B
+
+// ew: epilogue warp index (0 .. kEpiWarps-1; warps ew and ew+4 share a lane quarter)
+// origin(tile, m0, n0): first row / first channel of the tile in the output matrix
+// release(buf): arrive on the accumulator-empty barrier the MMA issuer waits on (called by one lane)
+// The TMA / bulk-group / mbarrier-arrive instructions of a warp are always issued by its elect.sync lane
+// (deterministic for a full mask), so the per-thread bulk async-groups stay with one thread.
+template <int kEpiWarps, class Origin, class Release>
+static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint32_t tmem_base, uint64_t* acc_full,
+                                                     uint8_t* epi_stage, uint64_t* res_bar, int ew, int lane,
+                                                     int tile_first, int tile_step, Origin origin, Release release) {
+    constexpr int kColGroups = kEpiWarps / 4;
+    const int quarter = (int)(threadIdx.x >> 5) & 3;     // TMEM lanes [32*quarter, +32) = rows of the tile
+    const int cg = ew >> 2;                              // this warp's chunks: cg, cg + kColGroups, ...
+    const int ecols = p.ecols;
+    const uint32_t erow = (uint32_t)ecols * (p.out_fp32 ? 4u : 2u);
+    const int n_chunks = p.BN / ecols;
+    const uint32_t sbufs = (uint32_t)p.stage_bufs;
+    uint8_t* my_stage = epi_stage + (size_t)ew * sbufs * kEpiSlice;
+    uint64_t* my_res = res_bar + ew * 2;
+    const int halves = p.out_fp32 ? 1 : (ecols + 31) / 32;              // 32 accumulator columns each
+
+    auto issue_res = [&](int tile, int c, uint32_t sb) {                 // elected lane only
+        int m0, n0;
+        origin(tile, m0, n0);
+        mbar_expect_tx(&my_res[sb], 32u * erow);
+        tma_load_2d(my_stage + sb * kEpiSlice, &p.tmRes, &my_res[sb], n0 + c * ecols, m0 + quarter * 32);
+    };
+    if (p.has_res && cg < n_chunks && tile_first < p.total_tiles && elect_one()) issue_res(tile_first, cg, 0u);
+
+    // NOTE: no early exit: after a time-out (*err_flag != 0) every wait returns at once, the loop
+    // drains quickly and the host sees the flag.
+    uint32_t g = 0;                                      // chunks this warp has handled
+    int local = 0;
+    for (int tile = tile_first; tile < p.total_tiles; tile += tile_step, ++local) {
+        const int buf = local & 1;
+        int m0, n0;
+        origin(tile, m0, n0);
+        mbar_wait(&acc_full[buf], (uint32_t)(local >> 1) & 1u, p.err_flag);
+        tc_fence_after();
+        if (cg >= n_chunks) {                            // tile narrower than the column groups: nothing to do
+            if (elect_one()) release(buf);
+            continue;
+        }
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.BN) + ((uint32_t)(quarter * 32) << 16);
+        for (int c = cg; c < n_chunks; c += kColGroups, ++g) {
+            const uint32_t sb = sbufs == 2 ? (g & 1u) : 0u;
+            uint8_t* slice = my_stage + sb * kEpiSlice;
+            if (!p.has_res) {                            // the store that last read this slice has drained
+                if (elect_one()) {
+                    if (sbufs == 2) bulk_wait_read_1();
+                    else bulk_wait_read_0();
+                }
+                __syncwarp();
+            }
+            for (int h = 0; h < halves; ++h) {
+                uint32_t v[32];
+                if (!(p.dbg & 32)) tmem_ld_32x32(tmem_acc + (uint32_t)(c * ecols + h * 32), v);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = (uint32_t)(j + lane);
+                }
+                if (c + kColGroups >= n_chunks && h == halves - 1) {
+                    // this warp's last TMEM read of the tile: hand the accumulator back to the MMA issuer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (elect_one()) release(buf);
+                }
+                if (p.has_res && h == 0)                 // shortcut operand of this chunk has landed in `slice`
+                    mbar_wait(&my_res[sb], (sbufs == 2 ? (g >> 1) : g) & 1u, p.err_flag);
+                const int nbase = n0 + c * ecols + h * 32;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + q * 8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + q * 8 + 4));
+                    float f[8];
+                    f[0] = __uint_as_float(v[q * 8 + 0]) + b0.x;
+                    f[1] = __uint_as_float(v[q * 8 + 1]) + b0.y;
+                    f[2] = __uint_as_float(v[q * 8 + 2]) + b0.z;
+                    f[3] = __uint_as_float(v[q * 8 + 3]) + b0.w;
+                    f[4] = __uint_as_float(v[q * 8 + 4]) + b1.x;
+                    f[5] = __uint_as_float(v[q * 8 + 5]) + b1.y;
+                    f[6] = __uint_as_float(v[q * 8 + 6]) + b1.z;
+                    f[7] = __uint_as_float(v[q * 8 + 7]) + b1.w;
+                    if (p.leaky) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = leaky01(f[j]);
+                    }
+                    if (p.out_fp32) {                    // 8 fp32 = two 16-byte chunks
+                        *reinterpret_cast<float4*>(slice + staged_offset(lane, q * 2, erow)) =
+                            make_float4(f[0], f[1], f[2], f[3]);
+                        *reinterpret_cast<float4*>(slice + staged_offset(lane, q * 2 + 1, erow)) =
+                            make_float4(f[4], f[5], f[6], f[7]);
+                    } else {
+                        const uint32_t off = staged_offset(lane, h * 4 + q, erow);
+                        if (p.has_res) {
+                            const uint4 r = *reinterpret_cast<const uint4*>(slice + off);
+                            f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
+                            f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+                            f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
+                            f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+                        }
+                        uint4 o;
+                        o.x = pack_bf16x2(f[0], f[1]);
+                        o.y = pack_bf16x2(f[2], f[3]);
+                        o.z = pack_bf16x2(f[4], f[5]);
+                        o.w = pack_bf16x2(f[6], f[7]);
+                        *reinterpret_cast<uint4*>(slice + off) = o;
+                    }
+                }
+            }
+            fence_async_smem();                          // generic-proxy writes -> visible to the TMA
+            __syncwarp();
+            if (elect_one()) {
+                if (!(p.dbg & 16)) tma_store_2d(&p.tmOut, slice, n0 + c * ecols, m0 + quarter * 32);
+                bulk_commit();
+                if (p.has_res) {                         // shortcut operand of this warp's next chunk
+                    int nt = tile, nc = c + kColGroups;
+                    if (nc >= n_chunks) {
+                        nt += tile_step;
+                        nc = cg;
+                    }
+                    if (nt < p.total_tiles) {
+                        if (sbufs == 2) bulk_wait_read_1();      // the store that last read the other slice
+                        else bulk_wait_read_0();
+                        issue_res(nt, nc, sbufs == 2 ? ((g + 1u) & 1u) : 0u);
+                    }
+                }
+            }
+        }
+    }
+    if (elect_one()) bulk_wait_all();
+    tc_fence_before();
+}
+
+}  // namespace rtod

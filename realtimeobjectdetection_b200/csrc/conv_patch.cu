@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
     if (warp == 6) {
         // ================= TMA producer A: one halo patch per (tile, channel slice) ====================
         // (its own warp: a wait for a free patch buffer must never hold back the weight stream)
-        if (lane == 0) {
+        if (elect_one()) {
             const int Q = my_tiles * p.cchunks;              // global sequence of (tile, channel slice)
             const uint32_t a_tx = (uint32_t)p.PH * p.PW * row_bytes;
             int buf = 0;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
         }
     } else if (warp == 0) {
         // ================= TMA producer B: weight tiles (ring), or the whole matrix once ===============
-        if (lane == 0) {
+        if (elect_one()) {
             if (p.b_resident) {
                 mbar_expect_tx(wres_bar, (uint32_t)num_kb * b_bytes);
                 for (int kb = 0; kb < num_kb; ++kb)
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_patch_kernel(const __grid_co
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             bool ok = true;
             int bs = 0, ab = 0;
             uint32_t bphase = 0, aphase = 0;

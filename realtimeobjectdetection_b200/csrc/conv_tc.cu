@@ -15,16 +15,17 @@
 //     producer through mbarriers and publishes each finished accumulator to the epilogue.
 //   * persistent CTAs (one per SM) loop over output tiles; the accumulator is double-buffered in
 //     TMEM (2 x BN columns) so the epilogue of one tile overlaps the MMAs of the next.
-//   * four epilogue warps read TMEM with tcgen05.ld (32 lanes x 32 columns), add the folded
-//     bias, apply leaky 0.1, add the shortcut operand (itself TMA-loaded into swizzled smem two
-//     chunks ahead), write bf16 (or the fp32 logits of a detection head) into a swizzled
-//     staging tile and hand it to a TMA store -- possibly into a channel slice of a
-//     route/concat buffer (src/darknet.py:285-288 becomes zero-copy); rows beyond M and channels
-//     beyond Cout are clipped by the descriptor.
+//   * four or eight epilogue warps (conv_epilogue.cuh), each an independent pipeline over its 32
+//     rows of the tile: tcgen05.ld (32 lanes x 32 columns), folded bias, leaky 0.1, shortcut operand
+//     (TMA-loaded one chunk ahead into the warp's own staging slice), bf16 (or the fp32 logits of a
+//     detection head) into the swizzled slice and a per-warp TMA store -- possibly into a channel
+//     slice of a route/concat buffer (src/darknet.py:285-288 becomes zero-copy); rows beyond M and
+//     channels beyond Cout are clipped by the descriptor.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue
-// (warp 2 also owns the TMEM allocation).  Every mbarrier wait is bounded: on a time-out the
-// kernel raises *err_flag and drains instead of hanging the GPU.
+// Warp roles (64 + 32*kEpiWarps threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. =
+// epilogue (warp 2 also owns the TMEM allocation).  Every mbarrier wait is bounded: on a time-out
+// the kernel raises *err_flag and drains instead of hanging the GPU.
+#include "conv_epilogue.cuh"
 #include "conv_tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -34,8 +35,7 @@ namespace rtod {
 
 namespace {
 
-constexpr int kThreads = 192;
-constexpr int kEpilogueWarps = 4;
+constexpr int threads_for(int epi_warps) { return 64 + 32 * epi_warps; }
 constexpr uint32_t kResidentLimit = 100 * 1024; // largest weight matrix kept resident in shared memory
 
 // =============================================================================================
@@ -43,25 +43,32 @@ constexpr uint32_t kResidentLimit = 100 * 1024; // largest weight matrix kept re
 // weight tile in L2).  The accumulator is double-buffered in TMEM, so the epilogue of tile i runs
 // while the tensor core already works on tile i+1, and the TMA producer runs ahead across tile
 // boundaries as far as the shared-memory ring allows.
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+template <int kEpiWarps>
+__global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long dbg_c0 = 0;
+    unsigned long long dbg_t0 = 0;
+    if ((p.dbg & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
+        dbg_c0 = clock64();
+        dbg_t0 = global_timer_ns();
+    }
     const uint32_t row_bytes = (uint32_t)p.BK * 2u;
     const uint32_t a_bytes = kBM * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
     const uint32_t stage_bytes = a_bytes + (p.b_resident ? 0u : b_bytes);
     // ring stages hold {A, B} tiles, or A tiles only when the whole weight matrix is resident
     uint8_t* b_resident = smem + (size_t)p.stages * stage_bytes;         // [num_kb][BN x BK] iff p.b_resident
-    uint8_t* out_stage = b_resident + (p.b_resident ? (size_t)p.ks * p.ks * p.cchunks * b_bytes : 0);
-    uint8_t* res_stage = out_stage + p.stage_bufs * kStageTile;          // [stage_bufs][kStageTile] shortcut operand
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(res_stage + (p.has_res ? p.stage_bufs * kStageTile : 0));
+    uint8_t* epi_stage = b_resident + (p.b_resident ? (size_t)p.ks * p.ks * p.cchunks * b_bytes : 0);
+    // [kEpiWarps][stage_bufs][kEpiSlice] epilogue staging slices (output, and shortcut operand in place)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + (size_t)kEpiWarps * p.stage_bufs * kEpiSlice);
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* acc_full = empty_bar + p.stages;          // [2] MMA -> epilogue
     uint64_t* acc_empty = acc_full + 2;                 // [2] epilogue -> MMA
-    uint64_t* res_full = acc_empty + 2;                 // [2] TMA (shortcut operand) -> epilogue
-    uint64_t* wres_bar = res_full + 2;                  // [1] resident weights have landed
+    uint64_t* res_full = acc_empty + 2;                 // [kEpiWarps][2] TMA (shortcut operand) -> epilogue warp
+    uint64_t* wres_bar = res_full + 2 * kEpiWarps;      // [1] resident weights have landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
 
     const int num_kb = p.ks * p.ks * p.cchunks;
@@ -79,9 +86,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], kEpilogueWarps);
-            mbar_init(&res_full[b], 1);
+            mbar_init(&acc_empty[b], kEpiWarps);
         }
+        for (int b = 0; b < 2 * kEpiWarps; ++b) mbar_init(&res_full[b], 1);
         mbar_init(wres_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -93,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
@@ -133,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
@@ -168,117 +175,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
         }
     } else {
-        // ================= epilogue: TMEM -> registers -> swizzled smem -> TMA store ============
-        // A chunk is 128 rows x one staging row (128 B: 64 bf16 or 32 fp32 channels; 64 B when the
-        // tile is only 32 bf16 channels wide).  Chunks are numbered continuously across tiles (g):
-        // staging buffer g & 1, so that the TMA store of chunk g and the TMA load of the shortcut
-        // operand of chunk g + 2 overlap the arithmetic of chunk g + 1.
-        const int quarter = warp & 3;                        // TMEM lanes [32*quarter, +32)
-        const int row = quarter * 32 + lane;                 // row of the tile this thread owns
-        const bool leader = warp == 2 && lane == 0;
-        const int ecols = p.ecols;
-        const uint32_t erow = (uint32_t)ecols * (p.out_fp32 ? 4u : 2u);
-        const int n_chunks = p.BN / ecols;
-        const uint32_t sbufs = (uint32_t)p.stage_bufs;       // staging tiles in flight: 2, or 1 to save smem
-        auto issue_res = [&](uint32_t g) {                   // leader only
-            const int tl = (int)(g / (uint32_t)n_chunks), c = (int)(g - (uint32_t)tl * n_chunks);
-            const int t = blockIdx.x + tl * gridDim.x;
-            if (t >= p.total_tiles) return;
-            const uint32_t sb = sbufs == 2 ? (g & 1u) : 0u;
-            mbar_expect_tx(&res_full[sb], kBM * erow);
-            tma_load_2d(res_stage + sb * kStageTile, &p.tmRes, &res_full[sb],
-                        (t / p.m_tiles) * p.BN + c * ecols, (t % p.m_tiles) * kBM);
-        };
-        if (p.has_res && leader) {
-            issue_res(0);
-            if (sbufs == 2) issue_res(1);
-        }
-        // NOTE: no early exit in this role: the named barriers below must be reached by all 128
-        // threads the same number of times.  After a time-out (*err_flag != 0) every wait returns
-        // at once, so the loop drains quickly and the host sees the flag.
-        uint32_t g = 0;
-        int local = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-            const int buf = local & 1;
-            const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
-            const int m0 = (tile % p.m_tiles) * kBM, n0 = (tile / p.m_tiles) * p.BN;
-            mbar_wait(&acc_full[buf], acc_phase, p.err_flag);
-            tc_fence_after();
-            const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.BN) + ((uint32_t)(quarter * 32) << 16);
-            for (int c = 0; c < n_chunks; ++c, ++g) {
-                const uint32_t sb = sbufs == 2 ? (g & 1u) : 0u;
-                uint8_t* ostage = out_stage + sb * kStageTile;
-                const uint8_t* rstage = res_stage + sb * kStageTile;
-                if (leader) {                                // the store that last used ostage has drained
-                    if (sbufs == 2) bulk_wait_read_1();
-                    else bulk_wait_read_0();
-                }
-                epi_barrier(1);
-                if (p.has_res) mbar_wait(&res_full[sb], (sbufs == 2 ? (g >> 1) : g) & 1u, p.err_flag);
-                const int halves = p.out_fp32 ? 1 : (ecols + 31) / 32;      // 32 accumulator columns each
-                for (int h = 0; h < halves; ++h) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tmem_acc + (uint32_t)(c * ecols + h * 32), v);
-                    if (c == n_chunks - 1 && h == halves - 1) {
-                        // last TMEM read of this tile: hand the accumulator back to the MMA issuer
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&acc_empty[buf]);
-                    }
-                    const int nbase = n0 + c * ecols + h * 32;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + q * 8));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + q * 8 + 4));
-                        float f[8];
-                        f[0] = __uint_as_float(v[q * 8 + 0]) + b0.x;
-                        f[1] = __uint_as_float(v[q * 8 + 1]) + b0.y;
-                        f[2] = __uint_as_float(v[q * 8 + 2]) + b0.z;
-                        f[3] = __uint_as_float(v[q * 8 + 3]) + b0.w;
-                        f[4] = __uint_as_float(v[q * 8 + 4]) + b1.x;
-                        f[5] = __uint_as_float(v[q * 8 + 5]) + b1.y;
-                        f[6] = __uint_as_float(v[q * 8 + 6]) + b1.z;
-                        f[7] = __uint_as_float(v[q * 8 + 7]) + b1.w;
-                        if (p.leaky) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] = leaky01(f[j]);
-                        }
-                        if (p.out_fp32) {                    // 8 fp32 = two 16-byte chunks
-                            *reinterpret_cast<float4*>(ostage + staged_offset(row, q * 2, erow)) =
-                                make_float4(f[0], f[1], f[2], f[3]);
-                            *reinterpret_cast<float4*>(ostage + staged_offset(row, q * 2 + 1, erow)) =
-                                make_float4(f[4], f[5], f[6], f[7]);
-                        } else {
-                            const uint32_t off = staged_offset(row, h * 4 + q, erow);
-                            if (p.has_res) {
-                                const uint4 r = *reinterpret_cast<const uint4*>(rstage + off);
-                                f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
-                                f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
-                                f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
-                                f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
-                            }
-                            uint4 o;
-                            o.x = pack_bf16x2(f[0], f[1]);
-                            o.y = pack_bf16x2(f[2], f[3]);
-                            o.z = pack_bf16x2(f[4], f[5]);
-                            o.w = pack_bf16x2(f[6], f[7]);
-                            *reinterpret_cast<uint4*>(ostage + off) = o;
-                        }
-                    }
-                }
-                fence_async_smem();                          // generic-proxy writes -> visible to the TMA
-                epi_barrier(2);
-                if (leader) {
-                    tma_store_2d(&p.tmOut, ostage, n0 + c * ecols, m0);   // rows >= M / cols >= Cout are clipped
-                    bulk_commit();
-                    if (p.has_res) issue_res(g + sbufs);
-                }
-            }
-        }
-        if (leader) bulk_wait_all();
-        tc_fence_before();
+        // ================= epilogue (conv_epilogue.cuh) =================
+        conv_epilogue<kEpiWarps>(
+            p, tmem_base, acc_full, epi_stage, res_full, warp - 2, lane, (int)blockIdx.x, (int)gridDim.x,
+            [&](int tile, int& m0, int& n0) {
+                m0 = (tile % p.m_tiles) * kBM;
+                n0 = (tile / p.m_tiles) * p.BN;
+            },
+            [&](int buf) { mbar_arrive(&acc_empty[buf]); });
     }
 
+    if ((p.dbg & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const long long dc = clock64() - dbg_c0;
+        const unsigned long long dt = global_timer_ns() - dbg_t0;
+        printf("%s M %d Cout %d ks %d: %lld clk in %llu ns = %.0f MHz\n", "conv_tc", p.M, p.Cout, p.ks, dc, dt, (double)dc * 1e3 / (double)dt);
+    }
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
@@ -304,7 +215,9 @@ bool conv_tc_supported(const ConvArgs& a) {
 int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     if (!conv_tc_supported(a)) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: unsupported convolution shape");
     launch->patch = 0;
+    launch->p.dbg = getenv("RTOD_CLK_DBG") ? 8 : 0;
     if (conv_patch_eligible(a)) return conv_patch_prepare(a, err_flag, launch);
+    if (conv_pair_eligible(a)) return conv_pair_prepare(a, err_flag, launch);
     static EncodeTiledFn encode_tiled = nullptr;
     static EncodeIm2colFn encode_im2col = nullptr;
     if (!encode_tiled) {
@@ -349,13 +262,11 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
     const uint32_t stage_bytes = (uint32_t)(kBM + BN) * BK * 2;
     p.has_res = a.res != nullptr;
-    p.ecols = a.out.fp32 ? 32 : (BN < 64 ? BN : 64);
     // ---- shared-memory plan --------------------------------------------------------------------
-    // Measured on B200: the TMA/mbarrier round trips of ONE CTA serialise (~250+ cycles per TMA
-    // operation whatever its size) while those of different CTAs on an SM overlap.  Tiles with
-    // little MMA work per TMA operation therefore run 2-4 CTAs per SM (TMEM: 2*BN columns each),
-    // with a single staging tile and without resident weights if that is what makes them fit;
-    // fat tiles (BN = 256) keep one CTA per SM and the deepest operand ring that fits.
+    // Thin tiles (little MMA work per TMA operation and per epilogue row) run 2-3 CTAs per SM (TMEM:
+    // 2*BN columns each) with four epilogue warps each, a single staging slice per warp and no
+    // resident weights if that is what makes them fit; fat tiles (BN = 256) keep one CTA per SM,
+    // eight epilogue warps and the deepest operand ring that fits.
     const uint32_t w_bytes = (uint32_t)BN * a.K * 2;
     const bool may_reside = a.Cout_pad == BN && w_bytes <= kResidentLimit && getenv("RTOD_TC_NO_RESIDENT") == nullptr;
     const uint32_t a_stage = (uint32_t)kBM * BK * 2;
@@ -364,24 +275,35 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     if (max_ctas > 3) max_ctas = 3;                      // measured: 3 beats 2 and 4 on the 208x208 layers
     int ctas_per_sm = 1, stages = 0;
     uint32_t fixed = 0, stage_bytes_eff = stage_bytes;
+    int epi_warps = 4;
+    const char* env_ew = getenv("RTOD_TC_EPI_WARPS");
+    const char* env_sb = getenv("RTOD_TC_SBUFS");
     for (int ctas = max_ctas; ctas >= 1 && stages == 0; --ctas) {
         const uint32_t cap = ctas == 1 ? kSmemLimit : (227u * 1024u) / ctas - 2048u;
-        for (int opt = 0; opt < 4 && stages == 0; ++opt) {          // prefer: resident + 2 staging tiles
+        int ew = (ctas == 1 && BN >= 128) ? 8 : 4;
+        if (env_ew && (atoi(env_ew) == 4 || (atoi(env_ew) == 8 && BN >= 128))) ew = atoi(env_ew);
+        for (int opt = 0; opt < 4 && stages == 0; ++opt) {          // prefer: resident + 2 staging slices
             const bool resident = may_reside && (opt & 1) == 0;
             const int sbufs = (opt & 2) ? 1 : 2;
             if ((opt & 1) && may_reside == false) continue;
-            if (ctas == 1 && sbufs == 1) continue;
-            const uint32_t fx = 1024 + sbufs * kStageTile * (p.has_res ? 2 : 1) + 512 + (resident ? w_bytes : 0);
+            if (env_sb && atoi(env_sb) != sbufs) continue;
+            const uint32_t fx = 1024 + ew * sbufs * kEpiSlice + 512 + (resident ? w_bytes : 0);
             const uint32_t sb = resident ? a_stage : stage_bytes;
             const int want = ctas == 1 ? 2 : 3;
             if (fx + want * sb > cap) continue;
             ctas_per_sm = ctas;
+            epi_warps = ew;
             p.b_resident = resident ? 1 : 0;
             p.stage_bufs = sbufs;
             fixed = fx;
             stage_bytes_eff = sb;
             stages = (int)((cap - fx) / sb);
         }
+    }
+    p.epi_warps = epi_warps;
+    {   // channels per epilogue chunk: one 128-byte staging row, narrower if the tile has fewer columns per group
+        const int per_group = BN / (epi_warps / 4);
+        p.ecols = a.out.fp32 ? 32 : (per_group < 64 ? per_group : 64);
     }
     if (stages == 0) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: shared memory budget exceeded");
     if (const char* e = getenv("RTOD_TC_STAGES")) {      // tuning knob
@@ -441,14 +363,14 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
             return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (weights, K=%d Cout_pad=%d) failed: %d", a.K,
                         a.Cout_pad, (int)r);
     }
-    // ---- epilogue: output tile store, shortcut operand load (same 128-row x 128-byte box) ----
+    // ---- epilogue: output slice store, shortcut operand load (same 32-row x 128-byte box) ----
     {
         const size_t esz = a.out.fp32 ? 4 : 2;
         const CUtensorMapDataType dt = a.out.fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
         const CUtensorMapSwizzle sw = p.ecols * esz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
         const cuuint64_t dims[2] = {(cuuint64_t)a.Cout, (cuuint64_t)M};
         const cuuint64_t strides[1] = {(cuuint64_t)a.out.pitch * esz};
-        const cuuint32_t box[2] = {(cuuint32_t)p.ecols, (cuuint32_t)kBM};
+        const cuuint32_t box[2] = {(cuuint32_t)p.ecols, 32};       // one epilogue warp's rows
         r = encode_tiled(&p.tmOut, dt, 2, a.out.ptr, dims, strides, box, estr1, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS)
@@ -463,14 +385,16 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
                 return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (shortcut operand) failed: %d", (int)r);
         }
     }
-    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      227 * 1024));
+    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return RTOD_OK;
 }
 
 int conv_tc_launch(const ConvTcLaunch& launch, cudaStream_t stream) {
+    if (launch.patch == 2) return conv_pair_launch(launch, stream);
     if (launch.patch) return conv_patch_launch(launch, stream);
-    conv_tc_kernel<<<launch.grid, kThreads, launch.smem_bytes, stream>>>(launch.p);
+    if (launch.p.epi_warps == 8) conv_tc_kernel<8><<<launch.grid, threads_for(8), launch.smem_bytes, stream>>>(launch.p);
+    else conv_tc_kernel<4><<<launch.grid, threads_for(4), launch.smem_bytes, stream>>>(launch.p);
     RTOD_LAUNCH_OK("conv_tc_kernel");
     return RTOD_OK;
 }

@@ -16,8 +16,10 @@ struct alignas(64) ConvTcParams {
     int* err_flag;              // device-side failure flag (pipeline time-out)
     int out_fp32, has_res;
     int b_resident;             // whole [BN x K] weight matrix lives in smem (single N tile, small K*BN)
-    int stage_bufs;             // epilogue staging tiles in flight (2; 1 when several CTAs share an SM)
-    int ecols;                  // channels per epilogue chunk (one staging row: 64 bf16 / 32 fp32)
+    int stage_bufs;             // staging slices per epilogue warp (2; 1 when shared memory is tight)
+    int epi_warps;              // 4 or 8 epilogue warps (kernel template argument)
+    int dbg;                    // conv_pair bring-up: 1 = MMA only (no loads), 2 = loads only (no MMA)
+    int ecols;                  // channels per epilogue chunk (one staging row: <= 64 bf16 / 32 fp32)
     int M, Cout;                // output pixels, real channels
     int leaky;
     int ks, cchunks;            // kernel size, Cin / BK
@@ -52,10 +54,15 @@ struct alignas(64) ConvPatchParams {
 struct ConvTcLaunch {           // host side: kernel parameters + launch geometry
     ConvTcParams p;
     ConvPatchParams pp;
-    int patch;                  // 1: launch conv_patch_kernel(pp), 0: conv_tc_kernel(p)
+    int patch;                  // 0: conv_tc_kernel(p), 1: conv_patch_kernel(pp), 2: conv_pair_kernel(p)
     dim3 grid;
     uint32_t smem_bytes;
 };
+
+// conv_pair.cu: cta_group::2 tiles (256 x 256 per CTA pair) for Cout % 256 == 0
+bool conv_pair_eligible(const ConvArgs& a);
+int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch);
+int conv_pair_launch(const ConvTcLaunch& launch, cudaStream_t stream);
 
 // conv_patch.cu
 bool conv_patch_eligible(const ConvArgs& a);

@@ -140,6 +140,84 @@ static __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// one lane of a fully converged warp; ptxas recognises the elected region as single-threaded and issues
+// TMA / tcgen05 instructions from it without a per-active-thread loop around every instruction
+static __device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// ---- thread-block cluster / cta_group::2 ("CTA pair") variants ----------------------------------------
+static __device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `p` (a pointer into this CTA's shared memory) in CTA `rank` of the cluster
+static __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+    uint32_t out;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(smem_u32(p)), "r"(rank));
+    return out;
+}
+static __device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+static __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr),
+                 "r"(bytes)
+                 : "memory");
+}
+static __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads issued by either CTA of a pair; the transaction bytes are credited to the barrier at
+// `bar_cluster_addr` (the leader CTA's), the data lands in the issuing CTA's own shared memory
+static __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr,
+                                                        int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+static __device__ __forceinline__ void tma_load_im2col_4d_pair(void* dst, const CUtensorMap* map,
+                                                               uint32_t bar_cluster_addr, int c, int w, int h, int n,
+                                                               uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(bar_cluster_addr), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
+static __device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+static __device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both CTAs, 128 rows each] * B[smem of both CTAs, N/2 rows each]
+static __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                      uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives (once the issued MMAs retire) on the barrier at this shared-memory offset in BOTH CTAs of the pair
+static __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+
 // shared-memory matrix descriptor, K-major operand whose rows are one swizzle span wide
 // (row_bytes = 32/64/128): start address, SBO = 8 rows, version 1, swizzle mode
 static __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t row_bytes) {

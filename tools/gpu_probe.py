@@ -203,6 +203,34 @@ def stage_layers():
         print("  decode %8.1f us" % (acc[n] * 1e3))
 
 
+def stage_clocks():
+    """SM clock measured in-kernel (rtod_sm_clock_probe on a side stream) while the forward runs"""
+    lib = _lib.load()
+    cfg, blocks, stream, state = make_network("yolov3", 3, "calibrated")
+    batch = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    model = Darknet(cfg, True)
+    model.load_state_dict({**model.state_dict(), **state})
+    model.eval()
+    x = torch.rand(batch, 3, 416, 416, device="cuda")
+    for _ in range(3):
+        model(x)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    out = torch.zeros(400, device="cuda")
+    if not os.environ.get("RTOD_NO_SIDE"):
+        _lib.check(lib.rtod_sm_clock_probe(out.data_ptr(), 400, 500, side.cuda_stream))   # 200 ms
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(25):
+        model(x)
+    e1.record()
+    torch.cuda.synchronize()
+    mhz = out.cpu().numpy()
+    print("forward %.3f ms/step; SM MHz per 0.5 ms window: first %s ... median of busy part %.0f, min %.0f, max %.0f" %
+          (e0.elapsed_time(e1) / 25, np.round(mhz[:6]).tolist(), float(np.median(mhz[20:300])), mhz[20:300].min(), mhz.max()))
+    print("  every 20th:", np.round(mhz[::20]).tolist())
+
+
 def stage_nmsbench():
     """BASELINE configs[3]: write_results on [256, 10647, 85] at 1/10/50 % density, C-ABI call only
     (CUDA events), plus the decode microbench on [256, 255, G, G] heads."""

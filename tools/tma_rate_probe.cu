@@ -136,8 +136,10 @@ int main() {
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     struct Case { const char* name; int mode, cbox, rows_or_w, h, depth, mult, variant; };
     const Case cases[] = {
-        {"2d 64x128 ring d4", MODE_2D, 64, 128, 0, 4, 1, 0}, {"2d 64x128 ring d8", MODE_2D, 64, 128, 0, 8, 1, 0},
-        {"2d 64x32 ring d8", MODE_2D, 64, 32, 0, 8, 1, 0}, {"2d 64x256 ring d4", MODE_2D, 64, 256, 0, 4, 1, 0},
+        {"2d 64x128 d8 x1", MODE_2D, 64, 128, 0, 8, 1, 0}, {"2d 64x128 d12 x1", MODE_2D, 64, 128, 0, 12, 1, 0},
+        {"im2col 64 d8 x1", MODE_IM2COL, 64, 0, 0, 8, 1, 0}, {"im2col 64 d12 x1", MODE_IM2COL, 64, 0, 0, 12, 1, 0},
+        {"im2col 64 d6 x2", MODE_IM2COL, 64, 0, 0, 6, 2, 0}, {"2d 64x128 d6 x2", MODE_2D, 64, 128, 0, 6, 2, 0},
+        {"2d 64x256 d6 x1", MODE_2D, 64, 256, 0, 6, 1, 0},
     };
     for (const Case& c : cases) {
         Args a{};
@@ -181,7 +183,7 @@ int main() {
         cudaMemcpy(hc.data(), dc, 1003 * 8, cudaMemcpyDeviceToHost);
         if (c.variant != 2) printf("   per-iteration clk (block 0): wait %.0f  arm %.0f  tma-issue %.0f\n", hc[1000] / (double)a.iters, hc[1001] / (double)a.iters, hc[1002] / (double)a.iters);
         double avg = 0;
-        for (long long v : hc) avg += (double)v / 148;
+        for (int b = 0; b < 148 * c.mult && b < 1000; ++b) avg += (double)hc[b] / (148 * c.mult);
         printf("%-30s depth %d  %7u B/load  %8.1f clk/load/cta  %6.1f B/clk/SM\n", c.name, c.depth, a.bytes, avg / a.iters,
                c.mult * a.bytes * (double)a.iters / avg);
     }
