@@ -33,12 +33,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef RTOD_TC_TRACE
     long long dbg_c0 = 0;
     unsigned long long dbg_t0 = 0;
     if ((p.dbg & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
         dbg_c0 = clock64();
         dbg_t0 = global_timer_ns();
     }
+#endif
     const uint32_t rank = cluster_ctarank();             // 0 = leader (issues the MMAs), 1 = peer
     const int tile_first = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
     const uint32_t row_bytes = (uint32_t)p.BK * 2u;
@@ -86,24 +88,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
-            long long dbg_wait = 0;
-            const long long dbg_start = clock64();
+            TRACE_DECL(dbg_wait);
+            TRACE_T0(dbg_start);
             for (int tile = tile_first; ok && tile < p.total_tiles; tile += tile_step) {
-                const int m0 = (2 * (tile % p.m_tiles) + (int)rank) * kBM;
-                const int nrow0 = (tile / p.m_tiles) * p.BN + (int)rank * (p.BN / 2);     // this CTA's half of B
+                const int n_tile = (int)fast_div((uint32_t)tile, p.fd_mtiles);
+                const int m0 = (2 * (tile - n_tile * p.m_tiles) + (int)rank) * kBM;
+                const int nrow0 = n_tile * p.BN + (int)rank * (p.BN / 2);                 // this CTA's half of B
                 int ow = 0, oh = 0, on = 0;
                 if (p.ks > 1) {
-                    ow = (m0 % p.Wo) * p.stride - p.pad;
-                    oh = ((m0 / p.Wo) % p.Ho) * p.stride - p.pad;
-                    on = m0 / (p.Wo * p.Ho);
+                    const int prow = (int)fast_div((uint32_t)m0, p.fd_wo);       // m0 / Wo
+                    on = (int)fast_div((uint32_t)m0, p.fd_howo);                 // m0 / (Ho * Wo)
+                    ow = (m0 - prow * p.Wo) * p.stride - p.pad;
+                    oh = (prow - on * p.Ho) * p.stride - p.pad;
                 }
                 int k0 = 0;
                 for (int tap = 0; ok && tap < p.ks * p.ks; ++tap) {
                     const uint16_t off_w = (uint16_t)(tap % p.ks), off_h = (uint16_t)(tap / p.ks);
                     for (int c0 = 0; c0 < p.cchunks * p.BK; c0 += p.BK, k0 += p.BK) {
-                        const long long w0 = clock64();
+                        TRACE_T0(w0);
                         if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag)) { ok = false; break; }
-                        dbg_wait += clock64() - w0;
+                        TRACE_ADD(dbg_wait, w0);
                         uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
                         const uint32_t lead_full = mapa_u32(&full_bar[stage], 0);
                         if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);   // both CTAs' bytes
@@ -117,8 +121,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
                     }
                 }
             }
+#ifdef RTOD_TC_TRACE
             if ((p.dbg & 8) && blockIdx.x < 2)
                 printf("  pair producer cta %d: total %lld clk, waiting for empty %lld\n", blockIdx.x, clock64() - dbg_start, dbg_wait);
+#endif
         }
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA only) =================
@@ -130,19 +136,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
             const uint64_t desc_tmpl = smem_desc(0u, row_bytes);
             const uint32_t ring_base = smem_u32(smem);
             const int ksteps = p.BK / 16;
-            long long dbg_wacc = 0, dbg_wfull = 0;
-            const long long dbg_start = clock64();
+            TRACE_DECL(dbg_wacc);
+            TRACE_DECL(dbg_wfull);
+            TRACE_T0(dbg_start);
             for (int tile = tile_first; ok && tile < p.total_tiles; tile += tile_step, ++local) {
                 const int buf = local & 1;
-                const long long w0 = clock64();
+                TRACE_T0(w0);
                 if (!mbar_wait(&acc_empty[buf], ((uint32_t)(local >> 1) & 1u) ^ 1u, p.err_flag)) break;
-                dbg_wacc += clock64() - w0;
+                TRACE_ADD(dbg_wacc, w0);
                 tc_fence_after();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.BN);
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    const long long w1 = clock64();
+                    TRACE_T0(w1);
                     if (!(p.dbg & 1) && !mbar_wait(&full_bar[stage], phase, p.err_flag)) { ok = false; break; }
-                    dbg_wfull += clock64() - w1;
+                    TRACE_ADD(dbg_wfull, w1);
                     tc_fence_after();
                     const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
                     uint64_t da = desc_tmpl | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
@@ -157,16 +164,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
                 }
                 umma_commit_pair(&acc_full[buf]);            // both CTAs' epilogues may read their half
             }
+#ifdef RTOD_TC_TRACE
             if ((p.dbg & 8) && blockIdx.x < 2)
                 printf("  pair mma cta %d: total %lld clk, waiting for full %lld, for acc_empty %lld\n", blockIdx.x, clock64() - dbg_start, dbg_wfull, dbg_wacc);
+#endif
         }
     } else {
         // ================= epilogue (conv_epilogue.cuh): each CTA stores its own 128 rows =================
         conv_epilogue<kEpilogueWarps>(
             p, tmem_base, acc_full, epi_stage, res_full, warp - 2, lane, tile_first, tile_step,
             [&](int tile, int& m0, int& n0) {
-                m0 = (2 * (tile % p.m_tiles) + (int)rank) * kBM;
-                n0 = (tile / p.m_tiles) * p.BN;
+                const int n_tile = (int)fast_div((uint32_t)tile, p.fd_mtiles);
+                m0 = (2 * (tile - n_tile * p.m_tiles) + (int)rank) * kBM;
+                n0 = n_tile * p.BN;
             },
             [&](int buf) {                               // the leader's MMA issuer waits for both CTAs' epilogues
                 if (rank == 0) mbar_arrive(&acc_empty[buf]);
@@ -174,11 +184,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
             });
     }
 
+#ifdef RTOD_TC_TRACE
     if ((p.dbg & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
         const long long dc = clock64() - dbg_c0;
         const unsigned long long dt = global_timer_ns() - dbg_t0;
         printf("%s M %d Cout %d ks %d: %lld clk in %llu ns = %.0f MHz\n", "conv_pair", p.M, p.Cout, p.ks, dc, dt, (double)dc * 1e3 / (double)dt);
     }
+#endif
     __syncthreads();
     cluster_sync_all();                                  // the peer may still be reading operands via the MMA
     if (warp == 2) {
@@ -226,6 +238,9 @@ int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     const int m_tiles = (int)((M + kBM - 1) / kBM);
     p.m_tiles = (m_tiles + 1) / 2;                        // tile PAIRS along M
     p.total_tiles = p.m_tiles * (a.Cout_pad / BN);
+    store_fastdiv(p.fd_mtiles, (uint32_t)p.m_tiles);
+    store_fastdiv(p.fd_wo, (uint32_t)a.out.W);
+    store_fastdiv(p.fd_howo, (uint32_t)(a.out.W * a.out.H));
     launch->patch = 2;
     launch->smem_bytes = stages * stage_bytes + fixed;
     RTOD_CUDA_OK(cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

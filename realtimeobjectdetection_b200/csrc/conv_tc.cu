@@ -50,12 +50,14 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef RTOD_TC_TRACE
     long long dbg_c0 = 0;
     unsigned long long dbg_t0 = 0;
     if ((p.dbg & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
         dbg_c0 = clock64();
         dbg_t0 = global_timer_ns();
     }
+#endif
     const uint32_t row_bytes = (uint32_t)p.BK * 2u;
     const uint32_t a_bytes = kBM * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
     const uint32_t stage_bytes = a_bytes + (p.b_resident ? 0u : b_bytes);
@@ -109,13 +111,17 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                 for (int kb = 0; kb < num_kb; ++kb)
                     tma_load_2d(b_resident + (size_t)kb * b_bytes, &p.tmB, wres_bar, kb * p.BK, 0);
             }
+            TRACE_DECL(dbg_wait);
+            TRACE_T0(dbg_start);
             for (int tile = blockIdx.x; ok && tile < p.total_tiles; tile += gridDim.x) {
-                const int m0 = (tile % p.m_tiles) * kBM, n0 = (tile / p.m_tiles) * p.BN;
+                const int n_tile = (int)fast_div((uint32_t)tile, p.fd_mtiles);
+                const int m0 = (tile - n_tile * p.m_tiles) * kBM, n0 = n_tile * p.BN;
                 int ow = 0, oh = 0, on = 0;
                 if (p.ks > 1) {                  // first output pixel of the tile -> input coords
-                    ow = (m0 % p.Wo) * p.stride - p.pad;
-                    oh = ((m0 / p.Wo) % p.Ho) * p.stride - p.pad;
-                    on = m0 / (p.Wo * p.Ho);
+                    const int prow = (int)fast_div((uint32_t)m0, p.fd_wo);       // m0 / Wo
+                    on = (int)fast_div((uint32_t)m0, p.fd_howo);                 // m0 / (Ho * Wo)
+                    ow = (m0 - prow * p.Wo) * p.stride - p.pad;
+                    oh = (prow - on * p.Ho) * p.stride - p.pad;
                 }
                 // taps outer, channel slices inner: all coordinates advance by additions (a lone
                 // thread retires one dependent instruction every ~5 cycles: divisions here would
@@ -124,7 +130,9 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                 for (int tap = 0; ok && tap < p.ks * p.ks; ++tap) {
                     const uint16_t off_w = (uint16_t)(tap % p.ks), off_h = (uint16_t)(tap / p.ks);
                     for (int c0 = 0; c0 < p.cchunks * p.BK; c0 += p.BK, k0 += p.BK) {
+                        TRACE_T0(w0);
                         if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag)) { ok = false; break; }
+                        TRACE_ADD(dbg_wait, w0);
                         uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
                         mbar_expect_tx(&full_bar[stage], stage_bytes);
                         if (p.ks > 1) tma_load_im2col_4d(a_dst, &p.tmA, &full_bar[stage], c0, ow, oh, on, off_w, off_h);
@@ -137,6 +145,11 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                     }
                 }
             }
+#ifdef RTOD_TC_TRACE
+            if ((p.dbg & 8) && blockIdx.x == 0)
+                printf("  tc producer: total %lld clk, waiting for empty %lld, tiles %d x %d k-blocks, stages %d, grid %d\n",
+                       clock64() - dbg_start, dbg_wait, (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x, num_kb, p.stages, (int)gridDim.x);
+#endif
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -148,15 +161,22 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
             const uint64_t desc_tmpl = smem_desc(0u, row_bytes);
             const uint32_t ring_base = smem_u32(smem), wres_base = smem_u32(b_resident);
             const int ksteps = p.BK / 16;
+            TRACE_DECL(dbg_wacc);
+            TRACE_DECL(dbg_wfull);
+            TRACE_T0(dbg_start);
             if (p.b_resident) ok = mbar_wait(wres_bar, 0u, p.err_flag);
             for (int tile = blockIdx.x; ok && tile < p.total_tiles; tile += gridDim.x, ++local) {
                 const int buf = local & 1;
                 const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
+                TRACE_T0(w0);
                 if (!mbar_wait(&acc_empty[buf], acc_phase ^ 1u, p.err_flag)) break;   // epilogue drained it
+                TRACE_ADD(dbg_wacc, w0);
                 tc_fence_after();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.BN);
                 for (int kb = 0; kb < num_kb; ++kb) {
+                    TRACE_T0(w1);
                     if (!mbar_wait(&full_bar[stage], phase, p.err_flag)) { ok = false; break; }
+                    TRACE_ADD(dbg_wfull, w1);
                     tc_fence_after();
                     // descriptors differ from the template only in the 14-bit start-address field
                     const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
@@ -173,23 +193,31 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                 }
                 umma_commit(&acc_full[buf]);                 // accumulator of this tile complete
             }
+#ifdef RTOD_TC_TRACE
+            if ((p.dbg & 8) && blockIdx.x == 0)
+                printf("  tc mma: total %lld clk, waiting for full %lld, for acc_empty %lld (BN %d BK %d resident %d epi_warps %d)\n",
+                       clock64() - dbg_start, dbg_wfull, dbg_wacc, p.BN, p.BK, p.b_resident, p.epi_warps);
+#endif
         }
     } else {
         // ================= epilogue (conv_epilogue.cuh) =================
         conv_epilogue<kEpiWarps>(
             p, tmem_base, acc_full, epi_stage, res_full, warp - 2, lane, (int)blockIdx.x, (int)gridDim.x,
             [&](int tile, int& m0, int& n0) {
-                m0 = (tile % p.m_tiles) * kBM;
-                n0 = (tile / p.m_tiles) * p.BN;
+                const int n_tile = (int)fast_div((uint32_t)tile, p.fd_mtiles);
+                m0 = (tile - n_tile * p.m_tiles) * kBM;
+                n0 = n_tile * p.BN;
             },
             [&](int buf) { mbar_arrive(&acc_empty[buf]); });
     }
 
+#ifdef RTOD_TC_TRACE
     if ((p.dbg & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
         const long long dc = clock64() - dbg_c0;
         const unsigned long long dt = global_timer_ns() - dbg_t0;
         printf("%s M %d Cout %d ks %d: %lld clk in %llu ns = %.0f MHz\n", "conv_tc", p.M, p.Cout, p.ks, dc, dt, (double)dc * 1e3 / (double)dt);
     }
+#endif
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
@@ -315,6 +343,9 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     p.stages = stages;
     p.m_tiles = (int)((M + kBM - 1) / kBM);
     p.total_tiles = p.m_tiles * (a.Cout_pad / BN);
+    store_fastdiv(p.fd_mtiles, (uint32_t)p.m_tiles);
+    store_fastdiv(p.fd_wo, (uint32_t)a.out.W);
+    store_fastdiv(p.fd_howo, (uint32_t)(a.out.W * a.out.H));
     launch->smem_bytes = stages * stage_bytes_eff + fixed;
     launch->grid = dim3((unsigned)(p.total_tiles < kNumSMs * ctas_per_sm ? p.total_tiles : kNumSMs * ctas_per_sm), 1, 1);
 

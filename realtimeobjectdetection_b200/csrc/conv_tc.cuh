@@ -18,7 +18,7 @@ struct alignas(64) ConvTcParams {
     int b_resident;             // whole [BN x K] weight matrix lives in smem (single N tile, small K*BN)
     int stage_bufs;             // staging slices per epilogue warp (2; 1 when shared memory is tight)
     int epi_warps;              // 4 or 8 epilogue warps (kernel template argument)
-    int dbg;                    // conv_pair bring-up: 1 = MMA only (no loads), 2 = loads only (no MMA)
+    int dbg;                    // bring-up switches (RTOD_PAIR_MODE / RTOD_CLK_DBG), 0 in production
     int ecols;                  // channels per epilogue chunk (one staging row: <= 64 bf16 / 32 fp32)
     int M, Cout;                // output pixels, real channels
     int leaky;
@@ -28,6 +28,7 @@ struct alignas(64) ConvTcParams {
     int tmem_cols;              // 2 * BN rounded up to a power of two
     int m_tiles, total_tiles;   // tile = m_tile + m_tiles * n_tile
     uint32_t idesc;             // tcgen05 instruction descriptor (bf16 x bf16 -> fp32, M=128, N=BN)
+    uint32_t fd_mtiles[3], fd_wo[3], fd_howo[3];   // FastDiv {mul, shift, d} for m_tiles, Wo, Ho*Wo (tc_ptx.cuh)
 };
 
 // 3x3 / stride 1 / pad 1 convolutions: "halo patch" variant (conv_patch.cu).  One TMA tiled load

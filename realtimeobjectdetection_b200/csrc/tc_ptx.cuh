@@ -35,22 +35,48 @@ static __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t par
         : "memory");
     return done != 0;
 }
-// bounded wait: false after a time-out or once another CTA has raised the failure flag
+// bounded wait: false after a time-out or once another CTA has raised the failure flag.  The flag (a
+// global load, ~700 cycles) and the clock are only consulted every 64 unsuccessful polls, so a barrier
+// that flips shortly after the first poll costs no memory round trip.
 static __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
-    if (mbar_try_wait(bar, parity)) return true;
-    if (*(volatile int*)err_flag != 0) return false;
-    const unsigned long long t0 = global_timer_ns();
     unsigned spins = 0;
+    unsigned long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 255u) == 0u) {
+        if ((++spins & 63u) == 0u) {
             if (*(volatile int*)err_flag != 0) return false;
-            if (global_timer_ns() - t0 > kWaitTimeoutNs) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kWaitTimeoutNs) {
                 atomicExch(err_flag, 2);
                 return false;
             }
         }
     }
     return true;
+}
+
+// role timing for bring-up builds (make TRACE=1, then RTOD_CLK_DBG=1): compiled out otherwise
+#ifdef RTOD_TC_TRACE
+#define TRACE_DECL(v) long long v = 0
+#define TRACE_T0(v) const long long v = clock64()
+#define TRACE_ADD(acc, t0) acc += clock64() - t0
+#else
+#define TRACE_DECL(v)
+#define TRACE_T0(v)
+#define TRACE_ADD(acc, t0)
+#endif
+
+// division by a runtime constant without the ~150-cycle integer divide (a lone producer / epilogue thread
+// pays full latency for every instruction): q = (umulhi(n, mul) + n) >> shift, exact for n < 2^31
+static inline void store_fastdiv(uint32_t (&dst)[3], uint32_t d) {     // into the kernel parameter block
+    uint32_t s = 0;
+    while ((1ull << s) < d) ++s;
+    dst[0] = (uint32_t)((((1ull << s) - d) << 32) / d + 1);
+    dst[1] = s;
+    dst[2] = d;
+}
+static __device__ __forceinline__ uint32_t fast_div(uint32_t n, const uint32_t (&f)[3]) {
+    return (uint32_t)(((unsigned long long)__umulhi(n, f[0]) + n) >> f[1]);
 }
 
 static __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,

@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(32) probe(const __grid_constant__ Args a, long
             for (int s = 0; s < a.depth; ++s) {
                 seed = seed * 1664525u + 1013904223u;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[s])), "r"(a.bytes) : "memory");
-                const int r0 = (int)((seed >> 8) % (uint32_t)(a.rows - 256));
-                const int cc0 = (int)((seed >> 4) % (uint32_t)(a.C / a.cbox)) * a.cbox;
+                const int r0 = (int)((seed >> 8) & 0x7FFFu);
+                const int cc0 = (int)((seed >> 4) & (uint32_t)(a.C / a.cbox - 1)) * a.cbox;
                 asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
                                  smem_u32(smem + (size_t)s * slot)), "l"(&a.map), "r"(smem_u32(&bars[s])), "r"(cc0), "r"(r0) : "memory");
             }
@@ -87,17 +87,17 @@ __global__ void __launch_bounds__(32) probe(const __grid_constant__ Args a, long
         t_arm += c3 - c2;
         void* dst = smem + (size_t)s * slot;
         if (a.mode == MODE_2D) {
-            const int r0 = (int)((seed >> 8) % (uint32_t)(a.rows - 256));
-            const int cc0 = (int)((seed >> 4) % (uint32_t)(a.C / a.cbox)) * a.cbox;
+            const int r0 = (int)((seed >> 8) & 0x7FFFu);
+            const int cc0 = (int)((seed >> 4) & (uint32_t)(a.C / a.cbox - 1)) * a.cbox;
             const long long c4 = clock64();
             asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
                              smem_u32(dst)), "l"(&a.map), "r"(smem_u32(&bars[s])), "r"(cc0), "r"(r0) : "memory");
             t_issue += clock64() - c4;
         } else {
-            const int n = (int)((seed >> 20) % (uint32_t)a.N);
-            const int y = (int)((seed >> 10) % (uint32_t)(a.H - 16));
-            const int x = (int)((seed >> 2) % (uint32_t)(a.W / 2));
-            const int c0 = (int)((seed >> 6) % (uint32_t)(a.C / a.cbox)) * a.cbox;
+            const int n = (int)((seed >> 20) & (uint32_t)(a.N - 1));
+            const int y = (int)((seed >> 10) & 31u);
+            const int x = (int)((seed >> 2) & 15u);
+            const int c0 = (int)((seed >> 6) & (uint32_t)(a.C / a.cbox - 1)) * a.cbox;
             if (a.mode == MODE_IM2COL)
                 asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
                              " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(dst)), "l"(&a.map),
@@ -136,9 +136,13 @@ int main() {
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     struct Case { const char* name; int mode, cbox, rows_or_w, h, depth, mult, variant; };
     const Case cases[] = {
-        {"2d 64x128 d8 x1", MODE_2D, 64, 128, 0, 8, 1, 0}, {"2d 64x128 d12 x1", MODE_2D, 64, 128, 0, 12, 1, 0},
+        {"2d 64x128 d1 x1", MODE_2D, 64, 128, 0, 1, 1, 0}, {"2d 64x128 d2 x1", MODE_2D, 64, 128, 0, 2, 1, 0},
+        {"2d 64x128 d4 x1", MODE_2D, 64, 128, 0, 4, 1, 0}, {"2d 64x128 d8 x1", MODE_2D, 64, 128, 0, 8, 1, 0},
+        {"2d 64x128 d12 x1", MODE_2D, 64, 128, 0, 12, 1, 0},
+        {"im2col 64 d1 x1", MODE_IM2COL, 64, 0, 0, 1, 1, 0}, {"im2col 64 d4 x1", MODE_IM2COL, 64, 0, 0, 4, 1, 0},
         {"im2col 64 d8 x1", MODE_IM2COL, 64, 0, 0, 8, 1, 0}, {"im2col 64 d12 x1", MODE_IM2COL, 64, 0, 0, 12, 1, 0},
-        {"im2col 64 d6 x2", MODE_IM2COL, 64, 0, 0, 6, 2, 0}, {"2d 64x128 d6 x2", MODE_2D, 64, 128, 0, 6, 2, 0},
+        {"im2col 64 d4 x3", MODE_IM2COL, 64, 0, 0, 4, 3, 0},
+        {"im2col 32 d8 x1", MODE_IM2COL, 32, 0, 0, 8, 1, 0}, {"im2col 32 d4 x3", MODE_IM2COL, 32, 0, 0, 4, 3, 0},
         {"2d 64x256 d6 x1", MODE_2D, 64, 256, 0, 6, 1, 0},
     };
     for (const Case& c : cases) {
