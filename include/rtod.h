@@ -117,6 +117,16 @@ int rtod_plan_forward(RtodPlan* plan, const float* x_nchw, float* pred, int trai
 int rtod_plan_forward_profile(RtodPlan* plan, const float* x_nchw, float* pred, int train, void* stream,
                               float* layer_ms_host, int* layer_kind_host);
 double rtod_plan_layer_flops(const RtodPlan* plan, int layer); /* 2*M*N*K of one convolution  */
+/* which kernel a bound plan runs for convolution `layer` (tests and profiling; not a reference call) */
+enum {
+    RTOD_CONV_NONE = 0,      /* not a convolution / plan not bound                               */
+    RTOD_CONV_STEM = 1,      /* stem.cu: 3-channel fp32 NCHW image -> NHWC bf16                  */
+    RTOD_CONV_TC = 2,        /* conv_tc.cu: tcgen05 implicit GEMM, one CTA per tile              */
+    RTOD_CONV_TC_PAIR = 3,   /* conv_pair.cu: tcgen05 cta_group::2, one CTA pair per 256x256 tile */
+    RTOD_CONV_TC_PATCH = 4,  /* conv_patch.cu: halo-patch 3x3 variant (opt-in)                   */
+    RTOD_CONV_SIMT = 5       /* conv_simt.cu: CUDA-core validation path (RTOD_PLAN_CONV_SIMT)     */
+};
+int rtod_plan_conv_backend(const RtodPlan* plan, int layer);
 
 /* Debug/validation: copy one layer's output to fp32 NCHW [batch, c, h, w].  Meaningful after a
  * forward of a plan created with RTOD_PLAN_KEEP_ALL (or for the last layer). */

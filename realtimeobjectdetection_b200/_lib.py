@@ -59,6 +59,7 @@ _PROTOTYPES = {
     "rtod_plan_forward": (_i, [_vp, _vp, _vp, _i, _vp]),
     "rtod_plan_forward_profile": (_i, [_vp, _vp, _vp, _i, _vp, ctypes.POINTER(_f), ctypes.POINTER(_i)]),
     "rtod_plan_layer_flops": (ctypes.c_double, [_vp, _i]),
+    "rtod_plan_conv_backend": (_i, [_vp, _i]),
     "rtod_plan_read_layer": (_i, [_vp, _i, _vp, _vp]),
     "rtod_plan_check": (_i, [_vp, _vp]),
     "rtod_yolo_decode": (_i, [_vp, _i, _i, _i, _i, _i, ctypes.POINTER(_f), _i, _vp, _vp]),

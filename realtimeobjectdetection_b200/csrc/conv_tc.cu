@@ -22,8 +22,8 @@
 //     slice of a route/concat buffer (src/darknet.py:285-288 becomes zero-copy); rows beyond M and
 //     channels beyond Cout are clipped by the descriptor.
 //
-// Warp roles (64 + 32*kEpiWarps threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. =
-// epilogue (warp 2 also owns the TMEM allocation).  Every mbarrier wait is bounded: on a time-out
+// Warp roles (96 + 32*kEpiWarps threads): warp 0 = TMA producer A, warp 1 = MMA issuer, warp 2 = TMA
+// producer B, warps 3.. = epilogue (warp 3 also owns the TMEM allocation).  Every mbarrier wait is bounded: on a time-out
 // the kernel raises *err_flag and drains instead of hanging the GPU.
 #include "conv_epilogue.cuh"
 #include "conv_tc.cuh"
@@ -35,7 +35,8 @@ namespace rtod {
 
 namespace {
 
-constexpr int threads_for(int epi_warps) { return 64 + 32 * epi_warps; }
+constexpr int kFirstEpiWarp = 3;                // warps 0, 1, 2: TMA producer A, MMA issuer, TMA producer B
+constexpr int threads_for(int epi_warps) { return 32 * (kFirstEpiWarp + epi_warps); }
 constexpr uint32_t kResidentLimit = 100 * 1024; // largest weight matrix kept resident in shared memory
 
 // =============================================================================================
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], p.b_resident ? 1 : 2);      // one arrive.expect_tx per producer thread
             mbar_init(&empty_bar[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -94,28 +95,26 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
         mbar_init(wres_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp == kFirstEpiWarp) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= TMA producer A: activations (im2col gather or [M, Cin] tiles) =================
+        // A and B have a producer thread each: issuing one im2col load occupies a thread for ~350 cycles
+        // (measured), so a single thread feeding both operands cannot keep up with thin tiles.
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
-            if (p.b_resident) {                  // single N tile: the whole [BN x K] weight matrix, once
-                mbar_expect_tx(wres_bar, (uint32_t)num_kb * b_bytes);
-                for (int kb = 0; kb < num_kb; ++kb)
-                    tma_load_2d(b_resident + (size_t)kb * b_bytes, &p.tmB, wres_bar, kb * p.BK, 0);
-            }
+            const int cin = p.cchunks * p.BK;
             TRACE_DECL(dbg_wait);
             TRACE_T0(dbg_start);
             for (int tile = blockIdx.x; ok && tile < p.total_tiles; tile += gridDim.x) {
                 const int n_tile = (int)fast_div((uint32_t)tile, p.fd_mtiles);
-                const int m0 = (tile - n_tile * p.m_tiles) * kBM, n0 = n_tile * p.BN;
+                const int m0 = (tile - n_tile * p.m_tiles) * kBM;
                 int ow = 0, oh = 0, on = 0;
                 if (p.ks > 1) {                  // first output pixel of the tile -> input coords
                     const int prow = (int)fast_div((uint32_t)m0, p.fd_wo);       // m0 / Wo
@@ -123,21 +122,19 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                     ow = (m0 - prow * p.Wo) * p.stride - p.pad;
                     oh = (prow - on * p.Ho) * p.stride - p.pad;
                 }
-                // taps outer, channel slices inner: all coordinates advance by additions (a lone
-                // thread retires one dependent instruction every ~5 cycles: divisions here would
-                // cost more than the tensor core needs for the whole k-block)
-                int k0 = 0;
-                for (int tap = 0; ok && tap < p.ks * p.ks; ++tap) {
-                    const uint16_t off_w = (uint16_t)(tap % p.ks), off_h = (uint16_t)(tap / p.ks);
-                    for (int c0 = 0; c0 < p.cchunks * p.BK; c0 += p.BK, k0 += p.BK) {
+                // taps outer, channel slices inner: all coordinates advance by additions (a lone thread retires
+                // one dependent instruction every ~5 cycles; one integer divide costs ~150)
+                for (int ky = 0; ok && ky < p.ks; ++ky)
+                for (int kx = 0; ok && kx < p.ks; ++kx) {
+                    for (int c0 = 0; c0 < cin; c0 += p.BK) {
                         TRACE_T0(w0);
                         if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag)) { ok = false; break; }
                         TRACE_ADD(dbg_wait, w0);
                         uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
-                        mbar_expect_tx(&full_bar[stage], stage_bytes);
-                        if (p.ks > 1) tma_load_im2col_4d(a_dst, &p.tmA, &full_bar[stage], c0, ow, oh, on, off_w, off_h);
+                        mbar_expect_tx(&full_bar[stage], a_bytes);
+                        if (p.ks > 1)
+                            tma_load_im2col_4d(a_dst, &p.tmA, &full_bar[stage], c0, ow, oh, on, (uint16_t)kx, (uint16_t)ky);
                         else tma_load_2d(a_dst, &p.tmA, &full_bar[stage], c0, m0);
-                        if (!p.b_resident) tma_load_2d(a_dst + a_bytes, &p.tmB, &full_bar[stage], k0, n0);
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1u;
@@ -150,6 +147,32 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                 printf("  tc producer: total %lld clk, waiting for empty %lld, tiles %d x %d k-blocks, stages %d, grid %d\n",
                        clock64() - dbg_start, dbg_wait, (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x, num_kb, p.stages, (int)gridDim.x);
 #endif
+        }
+    } else if (warp == 2) {
+        // ================= TMA producer B: weight tiles (ring), or the whole matrix once =================
+        if (elect_one()) {
+            if (p.b_resident) {                  // single N tile: the whole [BN x K] weight matrix, once
+                mbar_expect_tx(wres_bar, (uint32_t)num_kb * b_bytes);
+                for (int kb = 0; kb < num_kb; ++kb)
+                    tma_load_2d(b_resident + (size_t)kb * b_bytes, &p.tmB, wres_bar, kb * p.BK, 0);
+            } else {
+                int stage = 0;
+                uint32_t phase = 0;
+                bool ok = true;
+                const int ktot = num_kb * p.BK;
+                for (int tile = blockIdx.x; ok && tile < p.total_tiles; tile += gridDim.x) {
+                    const int n0 = (int)fast_div((uint32_t)tile, p.fd_mtiles) * p.BN;
+                    for (int k0 = 0; k0 < ktot; k0 += p.BK) {
+                        if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag)) { ok = false; break; }
+                        mbar_expect_tx(&full_bar[stage], b_bytes);
+                        tma_load_2d(smem + (size_t)stage * stage_bytes + a_bytes, &p.tmB, &full_bar[stage], k0, n0);
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -202,7 +225,7 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
     } else {
         // ================= epilogue (conv_epilogue.cuh) =================
         conv_epilogue<kEpiWarps>(
-            p, tmem_base, acc_full, epi_stage, res_full, warp - 2, lane, (int)blockIdx.x, (int)gridDim.x,
+            p, tmem_base, acc_full, epi_stage, res_full, warp - kFirstEpiWarp, lane, (int)blockIdx.x, (int)gridDim.x,
             [&](int tile, int& m0, int& n0) {
                 const int n_tile = (int)fast_div((uint32_t)tile, p.fd_mtiles);
                 m0 = (tile - n_tile * p.m_tiles) * kBM;
@@ -219,7 +242,7 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
     }
 #endif
     __syncthreads();
-    if (warp == 2) {
+    if (warp == kFirstEpiWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }

@@ -597,6 +597,15 @@ extern "C" double rtod_plan_layer_flops(const RtodPlan* p, int layer) {
     return 2.0 * (double)p->batch * nd.H * nd.W * nd.d.filters * nd.K;
 }
 
+extern "C" int rtod_plan_conv_backend(const RtodPlan* p, int layer) {
+    if (!p || !p->bound || layer < 0 || layer >= (int)p->nodes.size() || p->nodes[layer].d.type != RTOD_LAYER_CONV)
+        return RTOD_CONV_NONE;
+    const Node& nd = p->nodes[layer];
+    if (nd.stem) return RTOD_CONV_STEM;
+    if (!nd.use_tc) return RTOD_CONV_SIMT;
+    return nd.tc.patch == 2 ? RTOD_CONV_TC_PAIR : (nd.tc.patch == 1 ? RTOD_CONV_TC_PATCH : RTOD_CONV_TC);
+}
+
 extern "C" int rtod_plan_read_layer(RtodPlan* p, int layer, float* out_nchw, void* stream) {
     if (!p || !p->bound) return fail(RTOD_ERR_STATE, "rtod_plan_read_layer: plan is not bound");
     if (layer < 0 || layer >= (int)p->nodes.size() || !out_nchw)

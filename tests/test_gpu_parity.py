@@ -141,9 +141,9 @@ def _aligned(t):
     return (t.data_ptr() + 255) // 256 * 256
 
 
-def run_block(lib, descs, x, weights, flags=0):
+def run_block(lib, descs, x, weights, flags=0, backends=None):
     """Drive the C ABI directly: plan over `descs`, input x [B,C,H,W]; returns the fp32 NCHW output
-    of every layer."""
+    of every layer (and appends each layer's rtod_plan_conv_backend to `backends` if given)."""
     B, C, H, W = x.shape
     arr = (_lib.RtodLayerDesc * len(descs))(*descs)
     plan = ctypes.c_void_p()
@@ -168,6 +168,8 @@ def run_block(lib, descs, x, weights, flags=0):
     xd = x.cuda().contiguous()
     _lib.check(lib.rtod_plan_forward(plan, xd.data_ptr(), None, 0, None))
     _lib.check(lib.rtod_plan_check(plan, None))
+    if backends is not None:
+        backends.extend(lib.rtod_plan_conv_backend(plan, i) for i in range(len(descs)))
     outs = []
     for i in range(len(descs)):
         c, h, w = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
@@ -236,6 +238,45 @@ def test_conv_block_against_fp32_reference(lib, cin, cout, k, stride, H, batch, 
     assert frac_within(got, ref_q) == 1.0
     # against the exact fp32 block: bf16 operand rounding (2^-9 relative per operand)
     assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
+
+
+CONV_TC_PAIR, CONV_TC = 3, 2                # include/rtod.h RTOD_CONV_*
+
+# shapes large enough for the CTA-pair kernel (Cout % 256 == 0 and >= 60 pair tiles): an odd number of
+# 128-row tiles (the peer CTA of the last pair is entirely out of bounds), 1x1, stride 2, two N tiles
+PAIR_CASES = [(128, 256, 3, 1, 52, 6), (256, 512, 1, 1, 26, 12), (128, 256, 3, 2, 104, 6), (64, 512, 3, 1, 26, 11)]
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,H,batch", PAIR_CASES)
+def test_conv_block_cta_pair_kernel(lib, cin, cout, k, stride, H, batch):
+    rng = np.random.RandomState(cin + cout + k + stride + H)
+    x = torch.from_numpy(rng.randn(batch, cin, H, H).astype(np.float32))
+    w = rand_conv(rng, cin, cout, k)
+    backends = []
+    got = run_block(lib, [conv_desc(cout, k, stride)], x, {0: w}, 0, backends)[0]
+    assert backends == [CONV_TC_PAIR]           # the test is about conv_pair.cu, make sure it ran
+    ref_q = ref_block(x, w, k, stride, True, True)
+    assert got.shape == ref_q.shape
+    assert frac_within(got, ref_q) == 1.0
+
+@pytest.mark.gpu
+def test_residual_block_cta_pair_kernel(lib):
+    """shortcut operand TMA-loaded in place by the per-warp epilogue, on the CTA-pair kernel"""
+    rng = np.random.RandomState(23)
+    x = torch.from_numpy(rng.randn(6, 64, 52, 52).astype(np.float32))
+    w0, w1, w2 = rand_conv(rng, 64, 256, 3), rand_conv(rng, 256, 128, 1), rand_conv(rng, 128, 256, 3)
+    sc = _lib.RtodLayerDesc()
+    sc.type, sc.src0, sc.src1 = _lib.LAYER_SHORTCUT, 2, 0
+    backends = []
+    outs = run_block(lib, [conv_desc(256, 3, 1), conv_desc(128, 1, 1), conv_desc(256, 3, 1), sc], x,
+                     {0: w0, 1: w1, 2: w2}, 0, backends)
+    assert backends[0] == CONV_TC_PAIR and backends[2] == CONV_TC_PAIR and backends[1] == CONV_TC
+    y0 = ref_block(x, w0, 3, 1, True, True).bfloat16().float()
+    y1 = ref_block(y0, w1, 1, 1, True, True).bfloat16().float()
+    y3 = ref_block(y1, w2, 3, 1, True, True) + y0
+    assert frac_within(outs[0], y0) == 1.0
+    assert frac_within(outs[3], y3) >= 0.999
+    assert torch.equal(outs[2], outs[3])
 
 
 def test_conv_head_keeps_fp32_logits(lib):
