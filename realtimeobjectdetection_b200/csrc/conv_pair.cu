@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                          // everything above overlapped the previous layer's tail
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs) =================
@@ -326,13 +328,15 @@ int conv_pair_launch(const ConvTcLaunch& launch, cudaStream_t stream) {
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = launch.smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_pair_kernel, launch.p));
     return RTOD_OK;
 }

@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                          // everything above overlapped the previous layer's tail
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ================= TMA producer A: activations (im2col gather or [M, Cin] tiles) =================
@@ -447,9 +449,18 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
 int conv_tc_launch(const ConvTcLaunch& launch, cudaStream_t stream) {
     if (launch.patch == 2) return conv_pair_launch(launch, stream);
     if (launch.patch) return conv_patch_launch(launch, stream);
-    if (launch.p.epi_warps == 8) conv_tc_kernel<8><<<launch.grid, threads_for(8), launch.smem_bytes, stream>>>(launch.p);
-    else conv_tc_kernel<4><<<launch.grid, threads_for(4), launch.smem_bytes, stream>>>(launch.p);
-    RTOD_LAUNCH_OK("conv_tc_kernel");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = launch.grid;
+    cfg.blockDim = dim3((unsigned)threads_for(launch.p.epi_warps), 1, 1);
+    cfg.dynamicSmemBytes = launch.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    if (launch.p.epi_warps == 8) RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<8>, launch.p));
+    else RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<4>, launch.p));
     return RTOD_OK;
 }
 

@@ -105,23 +105,33 @@ yolo_decode_heads_kernel(DecodeHeads heads, int B, int N, int L, int train, int 
         const int n = A * L;
         int a = lane / L, attr = lane - a * L;               // (anchor, attribute) advance by additions
         const int step_a = 32 / L, step_attr = 32 - step_a * L;
-        for (int e = lane; e < n; e += 32) {
-            const float v = __ldg(src + e);
-            float r;
-            if (attr >= 4) {
-                r = sigmoid_f32(v);
-            } else if (attr < 2) {
-                r = sigmoid_f32(v);
-                if (!train) r = __fmul_rn(__fadd_rn(r, (float)(attr == 0 ? cx : cy)), stride);
-            } else {
-                r = train ? v : __fmul_rn(__fmul_rn(expf(v), attr == 2 ? heads.anchor_w[h][a] : heads.anchor_h[h][a]), stride);
+        for (int e0 = 0; e0 < n; e0 += 256) {                // 8 independent loads in flight per lane
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int e = e0 + lane + 32 * i;
+                v[i] = e < n ? __ldcs(src + e) : 0.0f;       // read once: streaming load
             }
-            dst[e] = r;
-            a += step_a;
-            attr += step_attr;
-            if (attr >= L) {
-                attr -= L;
-                ++a;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int e = e0 + lane + 32 * i;
+                // one exponential for every lane (no divergence): exp(v) for w/h, exp(-v) inside the sigmoid
+                const bool is_wh = attr == 2 || attr == 3;
+                const float t = expf(is_wh ? v[i] : -v[i]);
+                float r;
+                if (is_wh) {
+                    r = train ? v[i] : __fmul_rn(__fmul_rn(t, attr == 2 ? heads.anchor_w[h][a] : heads.anchor_h[h][a]), stride);
+                } else {
+                    r = __frcp_rn(__fadd_rn(1.0f, t));       // == sigmoid_f32(v)
+                    if (attr < 2 && !train) r = __fmul_rn(__fadd_rn(r, (float)(attr == 0 ? cx : cy)), stride);
+                }
+                if (e < n) __stcs(dst + e, r);
+                a += step_a;
+                attr += step_attr;
+                if (attr >= L) {
+                    attr -= L;
+                    ++a;
+                }
             }
         }
     }

@@ -1,6 +1,7 @@
 // tc_ptx.cuh -- inline-PTX wrappers (mbarrier, TMA, tcgen05/TMEM) and tensor-map host helpers shared by
 // the tcgen05 convolution kernels (conv_tc.cu: im2col / 1x1, conv_patch.cu: halo-patch 3x3).
 #pragma once
+#include <cstdlib>
 #include <cuda.h>
 
 #include "common.cuh"
@@ -68,6 +69,12 @@ static __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity,
 
 // division by a runtime constant without the ~150-cycle integer divide (a lone producer / epilogue thread
 // pays full latency for every instruction): q = (umulhi(n, mul) + n) >> shift, exact for n < 2^31
+// launch attribute for kernels that call pdl_wait(): allow them to start before the previous kernel ends
+static inline bool pdl_enabled() {
+    static const bool on = getenv("RTOD_NO_PDL") == nullptr;
+    return on;
+}
+
 static inline void store_fastdiv(uint32_t (&dst)[3], uint32_t d) {     // into the kernel parameter block
     uint32_t s = 0;
     while ((1ull << s) < d) ++s;
@@ -165,6 +172,12 @@ static __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+// programmatic dependent launch: the kernel's prologue (barrier init, TMEM allocation, descriptor prefetch)
+// overlaps the tail of the previous kernel in the stream; pdl_wait() returns once that kernel has completed
+// and its writes are visible, pdl_launch_dependents() lets the next kernel start its own prologue
+static __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+static __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // one lane of a fully converged warp; ptxas recognises the elected region as single-threaded and issues
 // TMA / tcgen05 instructions from it without a per-active-thread loop around every instruction
