@@ -73,6 +73,7 @@ typedef struct RtodPlan RtodPlan;
 /* plan flags */
 #define RTOD_PLAN_KEEP_ALL 1u     /* no buffer reuse: every layer output stays readable    */
 #define RTOD_PLAN_CONV_SIMT 2u    /* validation only: CUDA-core convs instead of tcgen05   */
+#define RTOD_PLAN_NO_AUTOTUNE 4u  /* bind: heuristic launch configurations, no timing runs */
 
 int rtod_abi_version(void);
 const char* rtod_last_error(void);
@@ -116,6 +117,10 @@ int rtod_plan_forward(RtodPlan* plan, const float* x_nchw, float* pred, int trai
  * 0 = no kernel (alias/fused), 1 = tcgen05 conv, 2 = CUDA-core conv, 3 = stem conv, 4 = other). */
 int rtod_plan_forward_profile(RtodPlan* plan, const float* x_nchw, float* pred, int train, void* stream,
                               float* layer_ms_host, int* layer_kind_host);
+/* Same forward, timed in two classes with events only where the stream switches between them: the
+ * tcgen05 convolution launches (conv_ms) and every other kernel (other_ms: stem, upsample, decode ...). */
+int rtod_plan_forward_segments(RtodPlan* plan, const float* x_nchw, float* pred, int train, void* stream,
+                               float* conv_ms, float* other_ms);
 double rtod_plan_layer_flops(const RtodPlan* plan, int layer); /* 2*M*N*K of one convolution  */
 /* which kernel a bound plan runs for convolution `layer` (tests and profiling; not a reference call) */
 enum {

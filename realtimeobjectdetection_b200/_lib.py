@@ -20,6 +20,7 @@ RTOD_MAX_ANCHORS = 8
 LAYER_CONV, LAYER_SHORTCUT, LAYER_ROUTE, LAYER_UPSAMPLE, LAYER_MAXPOOL, LAYER_YOLO = range(6)
 PLAN_KEEP_ALL = 1
 PLAN_CONV_SIMT = 2
+PLAN_NO_AUTOTUNE = 4
 
 
 class RtodError(RuntimeError):
@@ -58,6 +59,7 @@ _PROTOTYPES = {
     "rtod_plan_set_conv_weights": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp]),
     "rtod_plan_forward": (_i, [_vp, _vp, _vp, _i, _vp]),
     "rtod_plan_forward_profile": (_i, [_vp, _vp, _vp, _i, _vp, ctypes.POINTER(_f), ctypes.POINTER(_i)]),
+    "rtod_plan_forward_segments": (_i, [_vp, _vp, _vp, _i, _vp, ctypes.POINTER(_f), ctypes.POINTER(_f)]),
     "rtod_plan_layer_flops": (ctypes.c_double, [_vp, _i]),
     "rtod_plan_conv_backend": (_i, [_vp, _i]),
     "rtod_plan_read_layer": (_i, [_vp, _i, _vp, _vp]),

@@ -22,8 +22,8 @@
 //     slice of a route/concat buffer (src/darknet.py:285-288 becomes zero-copy); rows beyond M and
 //     channels beyond Cout are clipped by the descriptor.
 //
-// Warp roles (96 + 32*kEpiWarps threads): warp 0 = TMA producer A, warp 1 = MMA issuer, warp 2 = TMA
-// producer B, warps 3.. = epilogue (warp 3 also owns the TMEM allocation).  Every mbarrier wait is bounded: on a time-out
+// Warp roles (128 + 32*kEpiWarps threads): warp 0 = TMA producer A, warp 1 = MMA issuer, warp 2 = TMA
+// producer B, warp 3 = second producer A (thin tiles), warps 4.. = epilogue (warp 4 owns the TMEM allocation).  Every mbarrier wait is bounded: on a time-out
 // the kernel raises *err_flag and drains instead of hanging the GPU.
 #include "conv_epilogue.cuh"
 #include "conv_tc.cuh"
@@ -35,7 +35,7 @@ namespace rtod {
 
 namespace {
 
-constexpr int kFirstEpiWarp = 3;                // warps 0, 1, 2: TMA producer A, MMA issuer, TMA producer B
+constexpr int kFirstEpiWarp = 4;                // warps 0-3: TMA producer A, MMA issuer, TMA producer B, 2nd producer A
 constexpr int threads_for(int epi_warps) { return 32 * (kFirstEpiWarp + epi_warps); }
 constexpr uint32_t kResidentLimit = 100 * 1024; // largest weight matrix kept resident in shared memory
 
@@ -103,13 +103,17 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
     pdl_wait();                          // everything above overlapped the previous layer's tail
     pdl_launch_dependents();
 
-    if (warp == 0) {
+    if (warp == 0 || warp == 3) {
         // ================= TMA producer A: activations (im2col gather or [M, Cin] tiles) =================
-        // A and B have a producer thread each: issuing one im2col load occupies a thread for ~350 cycles
-        // (measured), so a single thread feeding both operands cannot keep up with thin tiles.
-        if (elect_one()) {
-            int stage = 0;
-            uint32_t phase = 0;
+        // A and B have producer threads of their own: issuing one im2col load occupies a thread for ~350
+        // cycles (measured), so a single thread feeding both operands cannot keep up with thin tiles; for
+        // the thinnest (k-block MMA time < 350 cycles) warps 0 and 3 alternate k-blocks.
+        const int me = warp == 0 ? 0 : 1;
+        if (me < p.a_producers && elect_one()) {
+            const int step = p.a_producers;                  // k-blocks q = me, me + step, ...
+            int stage = me % p.stages;
+            uint32_t phase = (uint32_t)(me / p.stages) & 1u;
+            int skip = me;                                   // k-blocks to skip before the next one of mine
             bool ok = true;
             const int cin = p.cchunks * p.BK;
             TRACE_DECL(dbg_wait);
@@ -129,6 +133,11 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                 for (int ky = 0; ok && ky < p.ks; ++ky)
                 for (int kx = 0; ok && kx < p.ks; ++kx) {
                     for (int c0 = 0; c0 < cin; c0 += p.BK) {
+                        if (skip) {
+                            --skip;
+                            continue;
+                        }
+                        skip = step - 1;
                         TRACE_T0(w0);
                         if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag)) { ok = false; break; }
                         TRACE_ADD(dbg_wait, w0);
@@ -137,8 +146,9 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                         if (p.ks > 1)
                             tma_load_im2col_4d(a_dst, &p.tmA, &full_bar[stage], c0, ow, oh, on, (uint16_t)kx, (uint16_t)ky);
                         else tma_load_2d(a_dst, &p.tmA, &full_bar[stage], c0, m0);
-                        if (++stage == p.stages) {
-                            stage = 0;
+                        stage += step;
+                        if (stage >= p.stages) {             // step <= stages: at most one wrap
+                            stage -= p.stages;
                             phase ^= 1u;
                         }
                     }
@@ -146,7 +156,7 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
             }
 #ifdef RTOD_TC_TRACE
             if ((p.dbg & 8) && blockIdx.x == 0)
-                printf("  tc producer: total %lld clk, waiting for empty %lld, tiles %d x %d k-blocks, stages %d, grid %d\n",
+                printf("  tc producer %d: total %lld clk, waiting for empty %lld, tiles %d x %d k-blocks, stages %d, grid %d\n", me,
                        clock64() - dbg_start, dbg_wait, (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x, num_kb, p.stages, (int)gridDim.x);
 #endif
         }
@@ -265,12 +275,15 @@ bool conv_tc_supported(const ConvArgs& a) {
     return true;
 }
 
-int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
+int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, const ConvTcChoice* force) {
     if (!conv_tc_supported(a)) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: unsupported convolution shape");
     launch->patch = 0;
     launch->p.dbg = getenv("RTOD_CLK_DBG") ? 8 : 0;
-    if (conv_patch_eligible(a)) return conv_patch_prepare(a, err_flag, launch);
-    if (conv_pair_eligible(a)) return conv_pair_prepare(a, err_flag, launch);
+    if (!force && conv_patch_eligible(a)) return conv_patch_prepare(a, err_flag, launch);
+    if (force ? force->pair == 1 : conv_pair_eligible(a)) {
+        if (!conv_pair_eligible(a)) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: CTA-pair kernel not applicable");
+        return conv_pair_prepare(a, err_flag, launch);
+    }
     static EncodeTiledFn encode_tiled = nullptr;
     static EncodeIm2colFn encode_im2col = nullptr;
     if (!encode_tiled) {
@@ -331,14 +344,19 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     int epi_warps = 4;
     const char* env_ew = getenv("RTOD_TC_EPI_WARPS");
     const char* env_sb = getenv("RTOD_TC_SBUFS");
+    // First fit in the order: most CTAs per SM, resident weights, two staging slices.  `force` (autotuning at
+    // plan-bind time, see conv_tc_autotune) pins one combination instead.
+    constexpr int kMaxStages = 12;
     for (int ctas = max_ctas; ctas >= 1 && stages == 0; --ctas) {
+        if (force && force->ctas != ctas) continue;
         const uint32_t cap = ctas == 1 ? kSmemLimit : (227u * 1024u) / ctas - 2048u;
         int ew = (ctas == 1 && BN >= 128) ? 8 : 4;
         if (env_ew && (atoi(env_ew) == 4 || (atoi(env_ew) == 8 && BN >= 128))) ew = atoi(env_ew);
-        for (int opt = 0; opt < 4 && stages == 0; ++opt) {          // prefer: resident + 2 staging slices
+        for (int opt = 0; opt < 4 && stages == 0; ++opt) {
             const bool resident = may_reside && (opt & 1) == 0;
             const int sbufs = (opt & 2) ? 1 : 2;
             if ((opt & 1) && may_reside == false) continue;
+            if (force && (force->resident != (resident ? 1 : 0) || force->sbufs != sbufs)) continue;
             if (env_sb && atoi(env_sb) != sbufs) continue;
             const uint32_t fx = 1024 + ew * sbufs * kEpiSlice + 512 + (resident ? w_bytes : 0);
             const uint32_t sb = resident ? a_stage : stage_bytes;
@@ -351,9 +369,13 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
             fixed = fx;
             stage_bytes_eff = sb;
             stages = (int)((cap - fx) / sb);
+            if (stages > kMaxStages) stages = kMaxStages;
         }
     }
     p.epi_warps = epi_warps;
+    launch->choice = ConvTcChoice{ctas_per_sm, p.b_resident, p.stage_bufs, 0};
+    // im2col issue costs a thread ~350 cycles: two alternating A producers when a k-block's MMAs take less
+    p.a_producers = (a.ks > 1 && (BK / 16) * (BN / 2) < 350 && getenv("RTOD_TC_ONE_A") == nullptr) ? 2 : 1;
     {   // channels per epilogue chunk: one 128-byte staging row, narrower if the tile has fewer columns per group
         const int per_group = BN / (epi_warps / 4);
         p.ecols = a.out.fp32 ? 32 : (per_group < 64 ? per_group : 64);
@@ -363,7 +385,6 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
         const int v = atoi(e);
         if (v >= 2 && v < stages) stages = v;
     }
-    if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     p.stages = stages;
     p.m_tiles = (int)((M + kBM - 1) / kBM);
@@ -443,6 +464,59 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     }
     RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return RTOD_OK;
+}
+
+// Plan-bind-time choice among the launch configurations that fit: each candidate is run on the layer's real
+// buffers (contents irrelevant: the kernels' timing does not depend on the data) and the fastest is kept.
+// All candidates accumulate over K in the same order, so the choice does not change the results.
+int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cudaStream_t stream) {
+    int rc = conv_tc_prepare(a, err_flag, launch, nullptr);              // heuristic choice = fallback
+    if (rc || launch->patch == 1 || getenv("RTOD_TC_NO_AUTOTUNE")) return rc;
+    cudaEvent_t e0, e1;
+    RTOD_CUDA_OK(cudaEventCreate(&e0));
+    RTOD_CUDA_OK(cudaEventCreate(&e1));
+    float best_ms = 1e30f;
+    ConvTcLaunch best = *launch;
+    ConvTcLaunch cand;
+    auto measure = [&](const ConvTcLaunch& l, float* ms) -> int {
+        *ms = 1e30f;
+        for (int rep = 0; rep < 3; ++rep) {                             // first run warms L2 / instruction cache
+            RTOD_CUDA_OK(cudaEventRecord(e0, stream));
+            int r = conv_tc_launch(l, stream);
+            if (r) return r;
+            RTOD_CUDA_OK(cudaEventRecord(e1, stream));
+            RTOD_CUDA_OK(cudaEventSynchronize(e1));
+            float t = 0.f;
+            RTOD_CUDA_OK(cudaEventElapsedTime(&t, e0, e1));
+            if (rep && t < *ms) *ms = t;
+        }
+        return RTOD_OK;
+    };
+    for (int pair = 1; pair >= 0; --pair)
+        for (int ctas = 3; ctas >= 1; --ctas)
+            for (int resident = 1; resident >= 0; --resident)
+                for (int sbufs = 2; sbufs >= 1; --sbufs) {
+                    if (pair && (ctas != 1 || resident != 0 || sbufs != 2)) continue;      // one pair configuration
+                    if (sbufs == 1 && a.res) continue;       // the shortcut operand is prefetched into the 2nd slice
+                    const ConvTcChoice c{ctas, resident, sbufs, pair};
+                    cand = ConvTcLaunch{};
+                    if (conv_tc_prepare(a, err_flag, &cand, &c) != RTOD_OK) continue;      // does not fit / apply
+                    float ms;
+                    if ((rc = measure(cand, &ms))) break;
+                    if (ms < best_ms) {
+                        best_ms = ms;
+                        best = cand;
+                    }
+                }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+    *launch = best;
+    if (getenv("RTOD_TC_TUNE_DBG"))
+        fprintf(stderr, "conv_tc_autotune: M %d Cin %d Cout %d ks %d s %d -> %s ctas %d resident %d sbufs %d stages %d (%.1f us)\n",
+                a.B * a.out.H * a.out.W, a.Cin, a.Cout, a.ks, a.stride, best.patch == 2 ? "pair" : "tc", best.choice.ctas,
+                best.choice.resident, best.choice.sbufs, best.p.stages, best_ms * 1e3f);
     return RTOD_OK;
 }
 

@@ -18,6 +18,7 @@ struct alignas(64) ConvTcParams {
     int b_resident;             // whole [BN x K] weight matrix lives in smem (single N tile, small K*BN)
     int stage_bufs;             // staging slices per epilogue warp (2; 1 when shared memory is tight)
     int epi_warps;              // 4 or 8 epilogue warps (kernel template argument)
+    int a_producers;            // 1 or 2 activation producer threads (2: they alternate k-blocks)
     int dbg;                    // bring-up switches (RTOD_PAIR_MODE / RTOD_CLK_DBG), 0 in production
     int ecols;                  // channels per epilogue chunk (one staging row: <= 64 bf16 / 32 fp32)
     int M, Cout;                // output pixels, real channels
@@ -52,7 +53,12 @@ struct alignas(64) ConvPatchParams {
     uint32_t idesc;
 };
 
+struct ConvTcChoice {           // one launch configuration of conv_tc_kernel (or the CTA-pair kernel)
+    int ctas, resident, sbufs, pair;
+};
+
 struct ConvTcLaunch {           // host side: kernel parameters + launch geometry
+    ConvTcChoice choice;
     ConvTcParams p;
     ConvPatchParams pp;
     int patch;                  // 0: conv_tc_kernel(p), 1: conv_patch_kernel(pp), 2: conv_pair_kernel(p)
@@ -73,7 +79,9 @@ int conv_patch_launch(const ConvTcLaunch& launch, cudaStream_t stream);
 // true if the tensor-core kernel tiles this convolution
 bool conv_tc_supported(const ConvArgs& a);
 // fills `p` (encodes the TMA descriptors); `err_flag` is a device int
-int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch);
+int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, const ConvTcChoice* force = nullptr);
+// conv_tc_prepare + timing of every configuration that fits (plan-bind time); keeps the fastest
+int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cudaStream_t stream);
 int conv_tc_launch(const ConvTcLaunch& launch, cudaStream_t stream);
 
 }  // namespace rtod

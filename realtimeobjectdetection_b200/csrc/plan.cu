@@ -407,7 +407,8 @@ int bind_layers(RtodPlan& p) {
         a.ks = nd.d.size; a.stride = nd.d.stride; a.pad = nd.d.pad; a.leaky = nd.d.leaky; a.K = nd.K;
         nd.use_tc = false;
         if (!nd.stem && !(p.flags & RTOD_PLAN_CONV_SIMT) && conv_tc_supported(a)) {
-            const int rc = conv_tc_prepare(a, p.err_flag, &nd.tc);
+            const int rc = (p.flags & RTOD_PLAN_NO_AUTOTUNE) ? conv_tc_prepare(a, p.err_flag, &nd.tc)
+                                                             : conv_tc_autotune(a, p.err_flag, &nd.tc, nullptr);
             if (rc) return rc;
             nd.use_tc = true;
         }
@@ -500,8 +501,24 @@ extern "C" int rtod_plan_set_conv_weights(RtodPlan* p, int layer, const float* w
 
 // one forward; when `ev` is non-null it holds n_layers + 2 events: ev[0] before the first launch,
 // ev[i + 1] after layer i, ev[n + 1] after the decode launch
+// `seg` (optional): events only where the stream switches between tcgen05 convolution launches (class 1) and
+// everything else (class 0) -- per-launch events would put a ~2-5 us gap after every one of the 74 convolutions
+struct Segments {
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> cls;
+};
+static int mark_segment(Segments* seg, int cls, cudaStream_t stream) {
+    if (!seg || (!seg->cls.empty() && seg->cls.back() == cls)) return RTOD_OK;
+    cudaEvent_t e;
+    RTOD_CUDA_OK(cudaEventCreate(&e));
+    RTOD_CUDA_OK(cudaEventRecord(e, stream));
+    seg->ev.push_back(e);
+    seg->cls.push_back(cls);
+    return RTOD_OK;
+}
+
 static int run_forward(RtodPlan* p, const float* x, float* pred, int train, cudaStream_t stream,
-                       cudaEvent_t* ev) {
+                       cudaEvent_t* ev, Segments* seg = nullptr) {
     if (!p || !p->bound) return fail(RTOD_ERR_STATE, "rtod_plan_forward: plan is not bound");
     if (!x) return fail(RTOD_ERR_BAD_ARG, "rtod_plan_forward: input is null");
     if (p->heads.count && !pred) return fail(RTOD_ERR_BAD_ARG, "rtod_plan_forward: pred is null");
@@ -517,6 +534,8 @@ static int run_forward(RtodPlan* p, const float* x, float* pred, int train, cuda
         if (ev && i > 0) RTOD_CUDA_OK(cudaEventRecord(ev[i], stream));
         if (nd.alias_of >= -1) continue;
         const RtodLayerDesc& d = nd.d;
+        if (d.type != RTOD_LAYER_ROUTE || nd.copy_concat)
+            if ((rc = mark_segment(seg, d.type == RTOD_LAYER_CONV && !nd.stem && nd.use_tc ? 1 : 0, stream))) return rc;
         rc = RTOD_OK;
         switch (d.type) {
         case RTOD_LAYER_CONV:
@@ -551,11 +570,13 @@ static int run_forward(RtodPlan* p, const float* x, float* pred, int train, cuda
         if (rc) return rc;
     }
     if (ev) RTOD_CUDA_OK(cudaEventRecord(ev[n], stream));
+    if (p->heads.count && (rc = mark_segment(seg, 0, stream))) return rc;
     if (p->heads.count) {
         rc = launch_decode_heads(p->heads, p->batch, p->n_rows, p->n_attrs, train, pred, stream);
         if (rc) return rc;
     }
     if (ev) RTOD_CUDA_OK(cudaEventRecord(ev[n + 1], stream));
+    if (seg && (rc = mark_segment(seg, -1, stream))) return rc;          // closing event
     return RTOD_OK;
 }
 
@@ -588,6 +609,27 @@ extern "C" int rtod_plan_forward_profile(RtodPlan* p, const float* x, float* pre
         }
     }
     for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+extern "C" int rtod_plan_forward_segments(RtodPlan* p, const float* x, float* pred, int train, void* stream_,
+                                          float* conv_ms, float* other_ms) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!p || !conv_ms || !other_ms) return fail(RTOD_ERR_BAD_ARG, "rtod_plan_forward_segments: null argument");
+    Segments seg;
+    int rc = run_forward(p, x, pred, train, stream, nullptr, &seg);
+    if (!rc) {
+        cudaError_t err = cudaStreamSynchronize(stream);
+        if (err != cudaSuccess) rc = fail(RTOD_ERR_CUDA, "segment timing sync failed: %s", cudaGetErrorString(err));
+    }
+    *conv_ms = 0.f;
+    *other_ms = 0.f;
+    for (size_t i = 0; i + 1 < seg.ev.size() && !rc; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, seg.ev[i], seg.ev[i + 1]);
+        (seg.cls[i] == 1 ? *conv_ms : *other_ms) += ms;
+    }
+    for (auto& e : seg.ev) cudaEventDestroy(e);
     return rc;
 }
 

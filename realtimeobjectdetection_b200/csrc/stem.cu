@@ -33,7 +33,7 @@ struct StemParams {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(512) stem_tma_kernel(const __grid_constant__ StemParams p) {
+__global__ void __launch_bounds__(448, 2) stem_tma_kernel(const __grid_constant__ StemParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 127u) & ~127u) - raw_addr);
@@ -80,39 +80,54 @@ __global__ void __launch_bounds__(512) stem_tma_kernel(const __grid_constant__ S
         bia[j][1] = __ldg(p.bias + 8 * j + 2 * t + 1);
     }
 
-    auto issue = [&](int local) {                     // thread 0: strip `local` of this CTA -> stage local % S
-        const int strip = blockIdx.x + local * gridDim.x;
-        if (strip >= p.total_strips || p.dbg == 1) return;
-        const int seg = strip % p.strips_per_row;
-        const int y = (strip / p.strips_per_row) % p.H;
-        const int b = strip / (p.strips_per_row * p.H);
-        const int s = local % kStemStages;
+    // strip -> (segment, row, image) advances by gridDim.x per iteration: carried additions instead of
+    // three integer divides (~450 cycles) on every warp's critical path
+    struct Pos { int seg, y, b; };
+    const int g_seg = (int)(gridDim.x % (unsigned)p.strips_per_row);
+    const int g_y = (int)((gridDim.x / (unsigned)p.strips_per_row) % (unsigned)p.H);
+    const int g_b = (int)(gridDim.x / (unsigned)(p.strips_per_row * p.H));
+    auto advance = [&](Pos& q) {
+        q.seg += g_seg;
+        const int c0 = q.seg >= p.strips_per_row;
+        q.seg -= c0 * p.strips_per_row;
+        q.y += g_y + c0;
+        const int c1 = q.y >= p.H;
+        q.y -= c1 * p.H;
+        q.b += g_b + c1;
+    };
+    Pos first;
+    first.seg = (int)(blockIdx.x % (unsigned)p.strips_per_row);
+    first.y = (int)((blockIdx.x / (unsigned)p.strips_per_row) % (unsigned)p.H);
+    first.b = (int)(blockIdx.x / (unsigned)(p.strips_per_row * p.H));
+    Pos ipos = first;                                 // thread 0: position of the next strip to load
+    int iloc = 0;
+    auto issue = [&]() {                              // thread 0: this CTA's next strip -> stage iloc % S
+        if (ipos.b >= p.B || p.dbg == 1) return;
+        const int s = iloc % kStemStages;
         mbar_expect_tx(&full[s], stage_bytes);
         // the innermost start coordinate must be 16-byte aligned: start 4 columns (not 1) left of the strip,
         // so shared-memory column j holds image column seg*SW - 4 + j
-        tma_load_3d(smem + s * stage_pitch, &p.tmX, &full[s], seg * p.SW - 4, y - 1, 3 * b);
+        tma_load_3d(smem + s * stage_pitch, &p.tmX, &full[s], ipos.seg * p.SW - 4, ipos.y - 1, 3 * ipos.b);
+        advance(ipos);
+        ++iloc;
     };
     if (threadIdx.x == 0)
-        for (int l = 0; l < kStemStages - 1; ++l) issue(l);
+        for (int l = 0; l < kStemStages - 1; ++l) issue();
 
     __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out.ptr);
-    for (int local = 0;; ++local) {
-        const int strip = blockIdx.x + local * gridDim.x;
-        if (strip >= p.total_strips) break;
-        const int s = local % kStemStages;
-        // stage (local + S - 1) % S was consumed in the previous iteration (all warps passed its barrier)
-        if (threadIdx.x == 0) issue(local + kStemStages - 1);
+    Pos pos = first;
+    int s = 0;
+    uint32_t parity = 0;
+    for (; pos.b < p.B; advance(pos)) {
+        // the stage consumed in the previous iteration is free (all warps passed its barrier)
+        if (threadIdx.x == 0) issue();
         if (p.dbg != 1) {
-            const uint32_t parity = (uint32_t)(local / kStemStages) & 1u;
             unsigned spins = 0;
             while (!mbar_try_wait(&full[s], parity))
                 if (++spins > (1u << 26)) break;     // never in practice; avoids a hard hang
         }
-        const int seg = strip % p.strips_per_row;
-        const int y = (strip / p.strips_per_row) % p.H;
-        const int b = strip / (p.strips_per_row * p.H);
-        const float* st = reinterpret_cast<const float*>(smem + s * stage_pitch);
-        const int x_first = seg * p.SW;
+        const int y = pos.y, b = pos.b;
+        const int x_first = pos.seg * p.SW;
         for (int tile = warp; tile < p.tiles_per_strip && p.dbg != 2; tile += nwarps) {
             const int px0 = tile * 16;
             if (x_first + px0 >= p.W) break;
@@ -166,6 +181,10 @@ __global__ void __launch_bounds__(512) stem_tma_kernel(const __grid_constant__ S
             }
         }
         __syncthreads();                              // every warp is done with stage s
+        if (++s == kStemStages) {
+            s = 0;
+            parity ^= 1u;
+        }
     }
 }
 
@@ -199,10 +218,11 @@ int launch_stem_tma(const float* x, int B, int H, int W, const float* w, const f
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (stem image) failed: %d", (int)r);
     int warps = p.tiles_per_strip;
-    if (warps > 16) warps = 16;
+    if (warps > 14) warps = (warps + 1) / 2;                    // two tiles per warp and strip
+    if (warps > 14) warps = 14;
     if (warps < 2) warps = 2;
     const size_t smem = (size_t)kStemStages * (((size_t)9 * p.box_w * 4 + 127) & ~(size_t)127) + kStemStages * 8 + 16 + 256;
-    const int per_sm = warps >= 8 ? 1 : 2;                       // register-bound: ~16-20 warps per SM
+    const int per_sm = 2;                                        // <= 72 registers/thread: two CTAs of <= 14 warps per SM
     int grid = kNumSMs * per_sm;
     if (grid > p.total_strips) grid = p.total_strips;
     if (Cout == 32) stem_tma_kernel<4><<<grid, warps * 32, smem, stream>>>(p);
