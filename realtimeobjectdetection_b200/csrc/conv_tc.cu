@@ -304,6 +304,11 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
         const int v = atoi(e);
         if (v >= 32 && v <= BN && a.Cout_pad % v == 0) BN = v;
     }
+    if (force && force->bn) {
+        if (force->bn > 256 || force->bn < 32 || a.Cout_pad % force->bn != 0 || (force->bn & (force->bn - 1)))
+            return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: forced N tile %d not applicable", force->bn);
+        BN = force->bn;
+    }
     if (a.Cout_pad % BN != 0 || BN % 32 != 0)
         return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: Cout_pad %d not tileable", a.Cout_pad);
     const long long M = (long long)a.B * a.out.H * a.out.W;
@@ -373,7 +378,7 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
         }
     }
     p.epi_warps = epi_warps;
-    launch->choice = ConvTcChoice{ctas_per_sm, p.b_resident, p.stage_bufs, 0};
+    launch->choice = ConvTcChoice{ctas_per_sm, p.b_resident, p.stage_bufs, 0, BN};
     // im2col issue costs a thread ~350 cycles: two alternating A producers when a k-block's MMAs take less
     p.a_producers = (a.ks > 1 && (BK / 16) * (BN / 2) < 350 && getenv("RTOD_TC_ONE_A") == nullptr) ? 2 : 1;
     {   // channels per epilogue chunk: one 128-byte staging row, narrower if the tile has fewer columns per group
@@ -493,13 +498,16 @@ int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cud
         }
         return RTOD_OK;
     };
+    const int bn_default = launch->patch == 2 ? 256 : launch->choice.bn;
     for (int pair = 1; pair >= 0; --pair)
+      for (int bn = 256; bn >= 64; bn >>= 1)
         for (int ctas = 3; ctas >= 1; --ctas)
             for (int resident = 1; resident >= 0; --resident)
                 for (int sbufs = 2; sbufs >= 1; --sbufs) {
-                    if (pair && (ctas != 1 || resident != 0 || sbufs != 2)) continue;      // one pair configuration
+                    if (pair && (bn != 256 || ctas != 1 || resident != 0 || sbufs != 2)) continue;   // one pair configuration
+                    if (!pair && (bn > bn_default || bn > a.Cout_pad)) continue;   // never wider than the heuristic's tile
                     if (sbufs == 1 && a.res) continue;       // the shortcut operand is prefetched into the 2nd slice
-                    const ConvTcChoice c{ctas, resident, sbufs, pair};
+                    const ConvTcChoice c{ctas, resident, sbufs, pair, bn};
                     cand = ConvTcLaunch{};
                     if (conv_tc_prepare(a, err_flag, &cand, &c) != RTOD_OK) continue;      // does not fit / apply
                     float ms;
@@ -514,8 +522,8 @@ int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cud
     if (rc) return rc;
     *launch = best;
     if (getenv("RTOD_TC_TUNE_DBG"))
-        fprintf(stderr, "conv_tc_autotune: M %d Cin %d Cout %d ks %d s %d -> %s ctas %d resident %d sbufs %d stages %d (%.1f us)\n",
-                a.B * a.out.H * a.out.W, a.Cin, a.Cout, a.ks, a.stride, best.patch == 2 ? "pair" : "tc", best.choice.ctas,
+        fprintf(stderr, "conv_tc_autotune: M %d Cin %d Cout %d ks %d s %d -> %s BN %d ctas %d resident %d sbufs %d stages %d (%.1f us)\n",
+                a.B * a.out.H * a.out.W, a.Cin, a.Cout, a.ks, a.stride, best.patch == 2 ? "pair" : "tc", best.choice.bn, best.choice.ctas,
                 best.choice.resident, best.choice.sbufs, best.p.stages, best_ms * 1e3f);
     return RTOD_OK;
 }

@@ -55,6 +55,7 @@ struct alignas(64) ConvPatchParams {
 
 struct ConvTcChoice {           // one launch configuration of conv_tc_kernel (or the CTA-pair kernel)
     int ctas, resident, sbufs, pair;
+    int bn;                     // N tile (0 = heuristic)
 };
 
 struct ConvTcLaunch {           // host side: kernel parameters + launch geometry
