@@ -186,7 +186,7 @@ def run_reference(args):
 # ------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import torch.distributed as dist
-    from realtimeobjectdetection_b200 import Darknet, _lib, write_results
+    from realtimeobjectdetection_b200 import Darknet, _lib, write_results, write_results_async
     from realtimeobjectdetection_b200.pipeline import DetectionPipeline
     from realtimeobjectdetection_b200.sharding import gather_detections
 
@@ -219,16 +219,31 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i):
-        pred = model(frames[i & 1])
-        det = write_results(pred, CLASSES, CONF, NMS)
+    pending = [None]
+
+    def collect():
+        """detections of the step enqueued before the current one (None at the first step)"""
+        if pending[0] is None:
+            return None
+        det = pending[0].result()
+        pending[0] = None
         if world > 1:
             det = gather_detections(det, rank * B)       # rows to rank 0 (NCCL), img index made global
+        return det
+
+    def step(i):
+        # streaming: step i is enqueued before step i-1's detection count is awaited, so the GPU never idles
+        # on the host; every step's detections are collected inside the timed region (flush after the loop)
+        pred = model(frames[i & 1])
+        handle = write_results_async(pred, CLASSES, CONF, NMS)
+        det = collect()
+        pending[0] = handle
         return det
 
     n_det = 0
     for i in range(W):
         step(i)
+    collect()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -237,8 +252,8 @@ def run_b200(args):
     barrier()
     t0 = time.time()
     e0.record()
-    for i in range(K):
-        det = step(i)
+    for i in range(K + 1):
+        det = step(i) if i < K else collect()            # K steps enqueued, K results collected
         if rank == 0 and not isinstance(det, int) and det is not None:
             n_det += det.size(0)
     e1.record()

@@ -11,7 +11,9 @@ calling it does, and there is no CPU fallback.
 """
 from .cfg import builtin_cfg, parse_cfg  # noqa: F401
 from .darknet import Darknet, DetectionLayer, EmptyLayer, MaxPoolStride1  # noqa: F401
-from .util import bbox_iou, confidence_mask, predict_transform, write_results  # noqa: F401
+from .util import (bbox_iou, confidence_mask, predict_transform, write_results,  # noqa: F401
+                   write_results_async)
 
 __all__ = ["Darknet", "DetectionLayer", "EmptyLayer", "MaxPoolStride1", "bbox_iou",
-           "confidence_mask", "predict_transform", "write_results", "builtin_cfg", "parse_cfg"]
+           "confidence_mask", "predict_transform", "write_results", "write_results_async", "builtin_cfg",
+           "parse_cfg"]

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import torch
 
-from .util import write_results
+from .util import write_results_async
 
 
 class DetectionPipeline:
@@ -58,6 +58,7 @@ class DetectionPipeline:
         except StopIteration:
             return
         k = 0
+        prev = None                                            # detections of the previous batch, not yet collected
         while pending is not None:
             nxt = None
             try:
@@ -66,11 +67,19 @@ class DetectionPipeline:
                 pass
             compute.wait_event(pending["ready"])
             pred = self.model(pending["buf"])
-            det = write_results(pred, self.num_class, self.confidence, self.nms_conf)
+            handle = write_results_async(pred, self.num_class, self.confidence, self.nms_conf)
             pending["free"].record(compute)
-            if not isinstance(det, int):
-                det = det.cpu()
-                self.d2h_bytes += det.numel() * 4
-            self.d2h_bytes += 4                                # the detection count
-            yield det
+            # this batch is in the stream: only now wait for the previous one (the GPU keeps working)
+            if prev is not None:
+                yield self._collect(prev)
+            prev = handle
             pending, k = nxt, k + 1
+        if prev is not None:
+            yield self._collect(prev)
+
+    def _collect(self, handle):
+        det = handle.result(to_host=True)
+        if not isinstance(det, int):
+            self.d2h_bytes += det.numel() * 4
+        self.d2h_bytes += 4                                    # the detection count
+        return det

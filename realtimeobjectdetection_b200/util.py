@@ -116,6 +116,75 @@ def predict_transform(prediction, inp_dim, anchors, num_class, CUDA, TRAIN=False
     return out.to(home)
 
 
+class PendingDetections:
+    """Handle of an enqueued ``write_results`` (see ``write_results_async``): the kernels and the copy of the
+    detection count to pinned host memory are in the stream, nothing has been synchronised yet."""
+
+    def __init__(self, rows, count_host, event, home, cap, device):
+        self._rows, self._count_host, self._event = rows, count_host, event
+        self._home, self._cap, self._device = home, cap, device
+
+    def result(self, to_host: bool = False):
+        """``[D, 8]`` rows or the int ``0`` (the reference's convention).  Waits only for the event recorded
+        after this call's kernels -- work enqueued later on the stream (the next batch) keeps running.
+        ``to_host``: copy the rows to the host on a side stream instead of the compute stream."""
+        self._event.synchronize()
+        d = int(self._count_host[0])
+        if d == 0:
+            return 0
+        if d > self._cap:
+            raise RuntimeError("write_results: %d detections exceed capacity %d" % (d, self._cap))
+        if to_host or self._home.type == "cpu":
+            side = _side_stream(self._device)
+            out = torch.empty(d, 8, dtype=torch.float32, pin_memory=True)
+            with torch.cuda.stream(side):
+                out.copy_(self._rows[:d], non_blocking=True)      # rows are final since `event`
+            side.synchronize()
+            return out
+        return self._rows[:d].clone()
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return _SIDE_STREAMS[key]
+
+
+def write_results_async(prediction, num_class, confidence=0.6, nms_conf=0.4) -> PendingDetections:
+    """``write_results`` split in two: this call enqueues scan + per-image NMS + emit and returns at once;
+    ``.result()`` yields what ``write_results`` returns.  A streaming loop enqueues the next batch's forward
+    before collecting, so the GPU never waits for the host (``DetectionPipeline``)."""
+    lib = _lib.load()
+    x, dev, home = _to_device(prediction)
+    if x.dim() != 3 or x.size(2) < 5 + int(num_class):
+        raise ValueError("write_results expects [B, N, >=5+num_class], got %s" % (tuple(x.shape),))
+    if x.size(2) != 5 + int(num_class):
+        x = x[:, :, :5 + int(num_class)].contiguous()      # reference slices 5:5+num_class (:279)
+    B, N, C = x.size(0), x.size(1), int(num_class)
+    cap = max(B * N, 1)
+    rows = torch.empty(cap, 8, dtype=torch.float32, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    event = torch.cuda.Event()
+    if B > 0 and N > 0:
+        nbytes = lib.rtod_write_results_workspace_bytes(B, N, C)
+        ws = _workspace(dev, nbytes + 256)
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        with torch.cuda.device(dev):
+            _lib.check(lib.rtod_write_results(x.data_ptr(), B, N, C, float(confidence), float(nms_conf),
+                                              rows.data_ptr(), cap, count.data_ptr(), ws_ptr, nbytes,
+                                              _stream_ptr(dev)))
+    count_host.copy_(count, non_blocking=True)
+    event.record(torch.cuda.current_stream(dev))
+    pending = PendingDetections(rows, count_host, event, home, cap, dev)
+    pending._keep = (x, count)                                 # alive until the kernels have run
+    return pending
+
+
 def write_results(prediction, num_class, confidence=0.6, nms_conf=0.4):
     """Threshold + per-image per-class greedy NMS -- src/util.py:242-346.
 
@@ -124,28 +193,4 @@ def write_results(prediction, num_class, confidence=0.6, nms_conf=0.4):
     test ``type(x) == int``).  Rows of one (image, class) with bit-equal objectness are ordered
     by row index (the reference's ``torch.sort`` leaves that order unspecified).
     """
-    lib = _lib.load()
-    x, dev, home = _to_device(prediction)
-    if x.dim() != 3 or x.size(2) < 5 + int(num_class):
-        raise ValueError("write_results expects [B, N, >=5+num_class], got %s" % (tuple(x.shape),))
-    if x.size(2) != 5 + int(num_class):
-        x = x[:, :, :5 + int(num_class)].contiguous()      # reference slices 5:5+num_class (:279)
-    B, N, C = x.size(0), x.size(1), int(num_class)
-    if B == 0 or N == 0:
-        return 0
-    nbytes = lib.rtod_write_results_workspace_bytes(B, N, C)
-    ws = _workspace(dev, nbytes + 256)
-    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
-    cap = B * N
-    rows = torch.empty(cap, 8, dtype=torch.float32, device=dev)
-    count = torch.empty(1, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(lib.rtod_write_results(x.data_ptr(), B, N, C, float(confidence), float(nms_conf),
-                                          rows.data_ptr(), cap, count.data_ptr(), ws_ptr, nbytes,
-                                          _stream_ptr(dev)))
-    d = int(count.item())                                   # the one host sync of the call
-    if d == 0:
-        return 0
-    if d > cap:
-        raise RuntimeError("write_results: %d detections exceed capacity %d" % (d, cap))
-    return rows[:d].clone().to(home)
+    return write_results_async(prediction, num_class, confidence, nms_conf).result()
