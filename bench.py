@@ -331,9 +331,10 @@ def run_b200(args):
                 "achieved_with_per_launch_events": per_launch_achieved,
                 "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tflops_sustained"],
-                # dram__bytes_read + dram__bytes_write of one captured launch (13x13 3x3 512->1024 layer at B=64,
-                # profiles/r1c_conv_tc_ncu.txt); its algorithmic bytes (in + weights + out, bf16) are 42.6 MB
-                "traffic": 43.85e6 if (args.cfg == "yolov3" and B == 64) else None,
+                # dram__bytes_read + dram__bytes_write of one captured conv_pair_kernel launch (13x13 3x3 512->1024
+                # layer at B=64, ncu --set full: 42.70 MB read + 1.33 MB written before the kernel ends; the output
+                # stays in L2); its algorithmic bytes (in + weights + out, bf16) are 42.6 MB
+                "traffic": 44.0e6 if (args.cfg == "yolov3" and B == 64) else None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s): kernel timed inside a long step"
                                % peaks["source"],
                 "launches_per_step": n_tc, "flops_per_step": tc_flops / reps,

@@ -145,7 +145,9 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
             }
         }
     }
-    if (elect_one()) bulk_wait_all();
+    // shared memory must stay valid until the last stores have READ it; their global writes are complete and
+    // visible at kernel completion, which is what the next layer (stream order / griddepcontrol.wait) waits for
+    if (elect_one()) bulk_wait_read_0();
     tc_fence_before();
 }
 

@@ -231,6 +231,28 @@ def stage_clocks():
     print("  every 20th:", np.round(mhz[::20]).tolist())
 
 
+def stage_ncufwd():
+    """one stream-launched forward + write_results between cudaProfilerStart/Stop (ncu --profile-from-start off):
+    the plan is bound (and autotuned) and warmed up outside the profiled range"""
+    lib = _lib.load()
+    cfg, blocks, stream, state = make_network("yolov3", 3, "calibrated")
+    batch = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    model = Darknet(cfg, True)
+    model.load_state_dict({**model.state_dict(), **state})
+    model.eval()
+    model.use_cuda_graph = False
+    x = torch.rand(batch, 3, 416, 416, device="cuda")
+    pred = model(x)
+    write_results(pred, 80, 0.5, 0.4)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    pred = model(x)
+    det = write_results(pred, 80, 0.5, 0.4)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    print("profiled one forward + write_results, B=%d, %d detections" % (batch, 0 if isinstance(det, int) else len(det)))
+
+
 def stage_nmsbench():
     """BASELINE configs[3]: write_results on [256, 10647, 85] at 1/10/50 % density, C-ABI call only
     (CUDA events), plus the decode microbench on [256, 255, G, G] heads."""
