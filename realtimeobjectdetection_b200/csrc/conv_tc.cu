@@ -29,6 +29,7 @@
 #include "conv_tc.cuh"
 #include "tc_ptx.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 
 namespace rtod {
@@ -476,6 +477,12 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
 // buffers (contents irrelevant: the kernels' timing does not depend on the data) and the fastest is kept.
 // All candidates accumulate over K in the same order, so the choice does not change the results.
 int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cudaStream_t stream) {
+    if (const char* f = getenv("RTOD_TC_FORCE")) {       // tests: "pair,bn,ctas,resident,sbufs" -> exactly that candidate
+        ConvTcChoice c{};
+        if (sscanf(f, "%d,%d,%d,%d,%d", &c.pair, &c.bn, &c.ctas, &c.resident, &c.sbufs) == 5 &&
+            conv_tc_prepare(a, err_flag, launch, &c) == RTOD_OK)
+            return RTOD_OK;                              // (a candidate that does not fit falls through to the default)
+    }
     int rc = conv_tc_prepare(a, err_flag, launch, nullptr);              // heuristic choice = fallback
     if (rc || launch->patch == 1 || getenv("RTOD_TC_NO_AUTOTUNE")) return rc;
     cudaEvent_t e0, e1;

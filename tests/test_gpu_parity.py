@@ -280,6 +280,31 @@ def test_residual_block_cta_pair_kernel(lib):
     assert torch.equal(outs[2], outs[3])
 
 
+# every launch configuration the bind-time autotuner may pick must give the same (correct) result:
+# "pair,bn,ctas,resident,sbufs" is forced through RTOD_TC_FORCE; combinations that do not fit a shape fall
+# back to the default, which is covered anyway
+FORCED = ["0,%d,%d,%d,%d" % (bn, c, r, s) for bn in (256, 128, 64) for c in (1, 2, 3) for r in (0, 1) for s in (1, 2)]
+FORCED.append("1,256,1,0,2")
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,H,batch", [(64, 128, 3, 1, 52, 3), (32, 64, 3, 2, 104, 2),
+                                                       (256, 256, 1, 1, 26, 12), (128, 256, 3, 1, 52, 6)])
+def test_conv_block_every_launch_configuration(lib, monkeypatch, cin, cout, k, stride, H, batch):
+    rng = np.random.RandomState(cin * 3 + cout + k + stride)
+    x = torch.from_numpy(rng.randn(batch, cin, H, H).astype(np.float32))
+    w = rand_conv(rng, cin, cout, k)
+    ref_q = ref_block(x, w, k, stride, True, True)
+    first = None
+    for force in FORCED:
+        monkeypatch.setenv("RTOD_TC_FORCE", force)
+        got = run_block(lib, [conv_desc(cout, k, stride)], x, {0: w})[0]
+        assert frac_within(got, ref_q) >= 0.9999, force   # (a bf16 rounding flip in a million elements is possible)
+        if first is None:
+            first = got
+        assert torch.equal(got, first), force           # same accumulation order in every configuration
+    monkeypatch.delenv("RTOD_TC_FORCE")
+
+
 def test_conv_head_keeps_fp32_logits(lib):
     """A convolution that only feeds a yolo layer stores fp32 (255 channels, no activation) and the
     single decode launch turns it into prediction rows."""
