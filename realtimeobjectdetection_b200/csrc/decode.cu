@@ -137,6 +137,66 @@ yolo_decode_heads_kernel(DecodeHeads heads, int B, int N, int L, int train, int 
     }
 }
 
+// Fast path of the same kernel for A*L <= 256 (YOLOv3: 255): which of a lane's eight elements are box
+// attributes (attr < 4) depends on the lane only, so the plain-sigmoid elements (249 of 255) run a short
+// uniform path -- exp(-v), 1 + t, correctly rounded reciprocal -- and the twelve special ones take the general
+// formula in the three iterations where they occur.  32-bit index arithmetic (B * cells < 2^31).
+template <bool kTrain>
+__global__ void __launch_bounds__(256)
+yolo_decode_heads_fast_kernel(DecodeHeads heads, unsigned total, int N, int L, unsigned cells_per_image,
+                              float* __restrict__ pred) {
+    const int lane = threadIdx.x & 31;
+    const unsigned warps = gridDim.x * (blockDim.x >> 5);
+    const int A = heads.num_anchors[0], n = A * L;
+    unsigned special = 0, valid = 0;                     // bit i: element lane + 32 i is a box attribute / exists
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int e = lane + 32 * i;
+        if (e < n) {
+            valid |= 1u << i;
+            if (e % L < 4) special |= 1u << i;
+        }
+    }
+    for (unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += warps) {
+        const unsigned b = w / cells_per_image;
+        unsigned cell = w - b * cells_per_image;
+        int h = 0;
+#pragma unroll
+        for (int k = 0; k < kMaxHeads - 1; ++k) {
+            const unsigned gg = (unsigned)(heads.grid[h] * heads.grid[h]);
+            if (h + 1 < heads.count && cell >= gg) {
+                cell -= gg;
+                ++h;
+            }
+        }
+        const unsigned G = (unsigned)heads.grid[h];
+        const unsigned cy = cell / G, cx = cell - cy * G;
+        const float stride = heads.stride[h];
+        const float* src = heads.raw[h] + ((size_t)b * G * G + cell) * heads.pitch[h] + lane;
+        float* dst = pred + ((size_t)b * N + heads.row_base[h] + (size_t)cell * A) * L + lane;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (valid >> i) & 1u ? __ldcs(src + 32 * i) : 0.0f;   // read once: streaming
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float r;
+            if ((special >> i) & 1u) {
+                const int e = lane + 32 * i, a = e / L, attr = e - a * L;
+                if (attr < 2) {
+                    r = sigmoid_f32(v[i]);
+                    if (!kTrain) r = __fmul_rn(__fadd_rn(r, (float)(attr == 0 ? cx : cy)), stride);
+                } else {
+                    r = kTrain ? v[i]
+                               : __fmul_rn(__fmul_rn(expf(v[i]), attr == 2 ? heads.anchor_w[h][a] : heads.anchor_h[h][a]), stride);
+                }
+            } else {
+                r = sigmoid_f32(v[i]);
+            }
+            if ((valid >> i) & 1u) __stcs(dst + 32 * i, r);
+        }
+    }
+}
+
 }  // namespace
 
 int launch_decode_heads(const DecodeHeads& heads, int B, int N, int L, int train, float* pred,
@@ -147,7 +207,14 @@ int launch_decode_heads(const DecodeHeads& heads, int B, int N, int L, int train
     if (total == 0 || N == 0) return RTOD_OK;
     long long blocks = (total + 7) / 8;
     if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
-    yolo_decode_heads_kernel<<<(unsigned)blocks, 256, 0, stream>>>(heads, B, N, L, train, cells, pred);
+    bool fast = total < (1ll << 31) && heads.num_anchors[0] * L <= 256;
+    for (int h = 1; h < heads.count; ++h) fast = fast && heads.num_anchors[h] == heads.num_anchors[0];
+    if (fast && train)
+        yolo_decode_heads_fast_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(heads, (unsigned)total, N, L, (unsigned)cells, pred);
+    else if (fast)
+        yolo_decode_heads_fast_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(heads, (unsigned)total, N, L, (unsigned)cells, pred);
+    else
+        yolo_decode_heads_kernel<<<(unsigned)blocks, 256, 0, stream>>>(heads, B, N, L, train, cells, pred);
     RTOD_LAUNCH_OK("yolo_decode_heads_kernel");
     return RTOD_OK;
 }
