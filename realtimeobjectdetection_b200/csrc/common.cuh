@@ -59,9 +59,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
-// logistic function with full-precision exp and IEEE division (reference: torch.sigmoid, fp32)
+// logistic function (reference: torch.sigmoid, fp32): full-precision exp, reciprocal by MUFU.RCP (<= 1 ulp;
+// 1 + exp(-v) is never denormal, so the flush-to-zero variant is exact in range).  The correctly rounded
+// reciprocal costs ~10 more instructions per element and made the decode kernels issue-bound.
 __device__ __forceinline__ float sigmoid_f32(float v) {
-    return __frcp_rn(__fadd_rn(1.0f, expf(-v)));          // correctly rounded reciprocal == 1.0f / x
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fadd_rn(1.0f, expf(-v))));
+    return r;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

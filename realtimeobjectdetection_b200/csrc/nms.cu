@@ -122,6 +122,7 @@ nms_scan_kernel(const float* __restrict__ pred, long long total_rows, int N, int
     __shared__ int slot_base[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // the image pass may be scheduled early
     const int stage_floats = rows_per_chunk * L;
     float* stage_buf[kScanStages];
     for (int s = 0; s < kScanStages; ++s)
@@ -304,6 +305,9 @@ nms_image_kernel(const float* __restrict__ pred, int N, int L, float conf, float
 
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x;
+    // programmatic dependent launch: this grid may start while the scan (or the light pass) drains
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     int n = cand_count[img];
     if (n > N) n = N;
     if (n <= 0) {
@@ -494,6 +498,7 @@ nms_emit_kernel(const float* __restrict__ pred, int B, int N, int L, float conf,
     __shared__ int s_part[8];
     __shared__ int s_offset;
     const int img = blockIdx.x, tid = threadIdx.x;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     int acc = 0;
     for (int i = tid; i < img; i += 256) acc += kept_count[i];
 #pragma unroll
@@ -667,23 +672,42 @@ extern "C" int rtod_write_results(const float* pred, int B, int N, int C, float 
     }
     {   // light pass: images with at most kLightCap candidates (and the empty ones)
         const int cap = lay.P < kLightCap ? lay.P : kLightCap;
-        nms_image_kernel<<<B, 512, (size_t)cap * 12 + cap / 8, stream>>>(pred, N, L, confidence, nms_conf, lay.P,
-                                                                        cand_count, keys, klist, kbits, pair,
-                                                                        kept_count, cap, -1, cap);
-        RTOD_LAUNCH_OK("nms_image_kernel (light)");
+        cudaLaunchAttribute pdl[1];
+        pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)B, 1, 1);
+        cfg.blockDim = dim3(512, 1, 1);
+        cfg.dynamicSmemBytes = (size_t)cap * 12 + cap / 8;
+        cfg.stream = stream;
+        cfg.attrs = pdl;
+        cfg.numAttrs = 1;
+        RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, nms_image_kernel, pred, N, L, confidence, nms_conf, lay.P,
+                                        (const int*)cand_count, keys, klist, kbits, pair, kept_count, cap, -1, cap));
         if (lay.P > kLightCap) {   // heavy pass: dense images
             const int hcap = lay.P < kSortSmemCap ? lay.P : kSortSmemCap;
-            nms_image_kernel<<<B, kImageThreads, (size_t)hcap * 12 + hcap / 8, stream>>>(
-                pred, N, L, confidence, nms_conf, lay.P, cand_count, keys, klist, kbits, pair, kept_count, hcap,
-                kLightCap, 0x7fffffff);
-            RTOD_LAUNCH_OK("nms_image_kernel (heavy)");
+            cfg.blockDim = dim3(kImageThreads, 1, 1);
+            cfg.dynamicSmemBytes = (size_t)hcap * 12 + hcap / 8;
+            RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, nms_image_kernel, pred, N, L, confidence, nms_conf, lay.P,
+                                            (const int*)cand_count, keys, klist, kbits, pair, kept_count, hcap,
+                                            (int)kLightCap, 0x7fffffff));
         }
     }
 
     // ---- emit ---------------------------------------------------------------------------------
-    nms_emit_kernel<<<B, 256, 0, stream>>>(pred, B, N, L, confidence, pair, kept_count, out_rows, cap,
-                                           out_count);
-    RTOD_LAUNCH_OK("nms_emit_kernel");
+    {
+        cudaLaunchAttribute pdl[1];
+        pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)B, 1, 1);
+        cfg.blockDim = dim3(256, 1, 1);
+        cfg.stream = stream;
+        cfg.attrs = pdl;
+        cfg.numAttrs = 1;
+        RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, nms_emit_kernel, pred, B, N, L, confidence, (const uint32_t*)pair,
+                                        (const int*)kept_count, out_rows, cap, out_count));
+    }
     return RTOD_OK;
 }
 
