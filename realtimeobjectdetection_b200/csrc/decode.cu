@@ -157,23 +157,39 @@ yolo_decode_heads_fast_kernel(DecodeHeads heads, unsigned total, int N, int L, u
             if (e % L < 4) special |= 1u << i;
         }
     }
-    for (unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += warps) {
-        const unsigned b = w / cells_per_image;
-        unsigned cell = w - b * cells_per_image;
-        int h = 0;
+    // every warp owns a contiguous run of cells: image, head and cell coordinates are located once (two
+    // integer divides) and then advanced by additions; a new head or image re-locates
+    const unsigned wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned per_warp = (total + warps - 1) / warps;
+    unsigned w = wid * per_warp;
+    const unsigned w_end = min(total, w + per_warp);
+    const float* src = nullptr;
+    float* dst = nullptr;
+    float stride = 0.f;
+    unsigned cx = 0, cy = 0, G = 1, left_in_head = 0;     // cells left in this (image, head) including the current
+    int h = 0, pitch = 0;
+    for (; w < w_end; ++w) {
+        if (left_in_head == 0) {
+            const unsigned b = w / cells_per_image;
+            unsigned cell = w - b * cells_per_image;
+            h = 0;
 #pragma unroll
-        for (int k = 0; k < kMaxHeads - 1; ++k) {
-            const unsigned gg = (unsigned)(heads.grid[h] * heads.grid[h]);
-            if (h + 1 < heads.count && cell >= gg) {
-                cell -= gg;
-                ++h;
+            for (int k = 0; k < kMaxHeads - 1; ++k) {
+                const unsigned gg = (unsigned)(heads.grid[h] * heads.grid[h]);
+                if (h + 1 < heads.count && cell >= gg) {
+                    cell -= gg;
+                    ++h;
+                }
             }
+            G = (unsigned)heads.grid[h];
+            cy = cell / G;
+            cx = cell - cy * G;
+            stride = heads.stride[h];
+            pitch = heads.pitch[h];
+            left_in_head = G * G - cell;
+            src = heads.raw[h] + ((size_t)b * G * G + cell) * pitch + lane;
+            dst = pred + ((size_t)b * N + heads.row_base[h] + (size_t)cell * A) * L + lane;
         }
-        const unsigned G = (unsigned)heads.grid[h];
-        const unsigned cy = cell / G, cx = cell - cy * G;
-        const float stride = heads.stride[h];
-        const float* src = heads.raw[h] + ((size_t)b * G * G + cell) * heads.pitch[h] + lane;
-        float* dst = pred + ((size_t)b * N + heads.row_base[h] + (size_t)cell * A) * L + lane;
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = (valid >> i) & 1u ? __ldcs(src + 32 * i) : 0.0f;   // read once: streaming
@@ -193,6 +209,13 @@ yolo_decode_heads_fast_kernel(DecodeHeads heads, unsigned total, int N, int L, u
                 r = sigmoid_f32(v[i]);
             }
             if ((valid >> i) & 1u) __stcs(dst + 32 * i, r);
+        }
+        src += pitch;
+        dst += n;
+        --left_in_head;
+        if (++cx == G) {
+            cx = 0;
+            ++cy;
         }
     }
 }
