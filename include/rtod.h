@@ -85,7 +85,9 @@ const char* rtod_last_error(void);
 int rtod_plan_create(const RtodLayerDesc* layers, int n_layers, int batch, int in_c, int in_h,
                      int in_w, int inp_dim, unsigned flags, RtodPlan** out_plan);
 void rtod_plan_destroy(RtodPlan* plan);
-size_t rtod_plan_workspace_bytes(const RtodPlan* plan);   /* activations + head logits     */
+size_t rtod_plan_workspace_bytes(const RtodPlan* plan);
+/* part of rtod_plan_workspace_bytes that is not activations: split-K partial tiles + arrival counters */
+size_t rtod_plan_scratch_bytes(const RtodPlan* plan);   /* activations + head logits     */
 size_t rtod_plan_weight_bytes(const RtodPlan* plan);      /* packed bf16 weights + biases  */
 int rtod_plan_num_rows(const RtodPlan* plan);             /* N of the [B, N, 5+C] output   */
 int rtod_plan_num_attrs(const RtodPlan* plan);            /* 5+C (0 if no yolo layer)      */

@@ -49,6 +49,7 @@ _PROTOTYPES = {
                               ctypes.POINTER(_vp)]),
     "rtod_plan_destroy": (None, [_vp]),
     "rtod_plan_workspace_bytes": (_sz, [_vp]),
+    "rtod_plan_scratch_bytes": (_sz, [_vp]),
     "rtod_plan_weight_bytes": (_sz, [_vp]),
     "rtod_plan_num_rows": (_i, [_vp]),
     "rtod_plan_num_attrs": (_i, [_vp]),

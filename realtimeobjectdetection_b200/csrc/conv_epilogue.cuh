@@ -151,4 +151,135 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
     tc_fence_before();
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Split-K variant (small batches: a 13x13x1024 layer at batch 1 has two M tiles and 72 serial k-blocks).
+// `split` CTAs share one output tile, each accumulating a slice of K.  Every CTA dumps its raw fp32
+// accumulator to scratch[tile][slice][128][BN]; a per-tile counter elects the LAST CTA to arrive, which
+// sums the `split` partials in slice order (deterministic, independent of arrival order) and runs the
+// normal bias / leaky / shortcut / store path.  work(i, tile, slice) enumerates this CTA's work items.
+template <int kEpiWarps, class Work, class Origin, class Release>
+static __device__ __forceinline__ void conv_epilogue_split(const ConvTcParams& p, uint32_t tmem_base,
+                                                           uint64_t* acc_full, uint8_t* epi_stage, uint64_t* res_bar,
+                                                           int* s_last, int ew, int lane, Work work, Origin origin,
+                                                           Release release) {
+    constexpr int kColGroups = kEpiWarps / 4;
+    const int quarter = (int)(threadIdx.x >> 5) & 3;
+    const int cg = ew >> 2;
+    const int ecols = p.ecols;
+    const uint32_t erow = (uint32_t)ecols * (p.out_fp32 ? 4u : 2u);
+    const int n_chunks = p.BN / ecols;
+    uint8_t* slice = epi_stage + (size_t)ew * p.stage_bufs * kEpiSlice;   // one staging slice is enough here
+    uint64_t* my_res = res_bar + ew * 2;
+    const int halves = p.out_fp32 ? 1 : (ecols + 31) / 32;
+    const int S = p.split_k;
+    const int row = quarter * 32 + lane;
+    uint32_t res_uses = 0;                               // completed phases of my_res[0]
+    int tile, slice_k;
+    for (int local = 0; work(local, tile, slice_k); ++local) {
+        const int buf = local & 1;
+        int m0, n0;
+        origin(tile, m0, n0);
+        mbar_wait(&acc_full[buf], (uint32_t)(local >> 1) & 1u, p.err_flag);
+        tc_fence_after();
+        // ---- pass 1: raw accumulator -> scratch ----------------------------------------------------------
+        if (cg < n_chunks) {
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.BN) + ((uint32_t)(quarter * 32) << 16);
+            float* part = p.split_scratch + ((size_t)(tile * S + slice_k) * kBM + row) * p.BN;
+            for (int c = cg; c < n_chunks; c += kColGroups)
+                for (int h = 0; h < halves; ++h) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_acc + (uint32_t)(c * ecols + h * 32), v);
+                    float4* dst = reinterpret_cast<float4*>(part + c * ecols + h * 32);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        __stcg(dst + q, make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+                                                    __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3])));
+                }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (elect_one()) release(buf);
+        // ---- which CTA finishes the tile? ----------------------------------------------------------------
+        __threadfence();                                 // partials visible before the counter moves
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");
+        if (ew == 0 && lane == 0) {
+            const int old = atomicAdd(&p.split_count[tile], 1);
+            *s_last = old == S - 1;
+            if (old == S - 1) p.split_count[tile] = 0;   // ready for the next forward
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");
+        const bool last = *s_last != 0;
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");       // s_last may be rewritten
+        if (!last || cg >= n_chunks) continue;
+        __threadfence();
+        // ---- pass 2 (last arriver): sum the partials in slice order, then the normal epilogue ------------
+        const float* part0 = p.split_scratch + ((size_t)(tile * S) * kBM + row) * p.BN;
+        for (int c = cg; c < n_chunks; c += kColGroups) {
+            if (elect_one()) {
+                bulk_wait_read_0();                      // the store that last read `slice` has drained
+                if (p.has_res) {
+                    mbar_expect_tx(&my_res[0], 32u * erow);
+                    tma_load_2d(slice, &p.tmRes, &my_res[0], n0 + c * ecols, m0 + quarter * 32);
+                }
+            }
+            __syncwarp();
+            if (p.has_res) {
+                mbar_wait(&my_res[0], res_uses & 1u, p.err_flag);
+                ++res_uses;
+            }
+            for (int h = 0; h < halves; ++h) {
+                const int nbase = n0 + c * ecols + h * 32;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + q * 8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + q * 8 + 4));
+                    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    for (int s = 0; s < S; ++s) {
+                        const float4* src =
+                            reinterpret_cast<const float4*>(part0 + (size_t)s * kBM * p.BN + c * ecols + h * 32 + q * 8);
+                        const float4 x0 = __ldcg(src), x1 = __ldcg(src + 1);
+                        f[0] += x0.x; f[1] += x0.y; f[2] += x0.z; f[3] += x0.w;
+                        f[4] += x1.x; f[5] += x1.y; f[6] += x1.z; f[7] += x1.w;
+                    }
+                    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                    f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                    if (p.leaky) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = leaky01(f[j]);
+                    }
+                    if (p.out_fp32) {
+                        *reinterpret_cast<float4*>(slice + staged_offset(lane, q * 2, erow)) =
+                            make_float4(f[0], f[1], f[2], f[3]);
+                        *reinterpret_cast<float4*>(slice + staged_offset(lane, q * 2 + 1, erow)) =
+                            make_float4(f[4], f[5], f[6], f[7]);
+                    } else {
+                        const uint32_t off = staged_offset(lane, h * 4 + q, erow);
+                        if (p.has_res) {
+                            const uint4 r = *reinterpret_cast<const uint4*>(slice + off);
+                            f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
+                            f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+                            f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
+                            f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+                        }
+                        uint4 o;
+                        o.x = pack_bf16x2(f[0], f[1]);
+                        o.y = pack_bf16x2(f[2], f[3]);
+                        o.z = pack_bf16x2(f[4], f[5]);
+                        o.w = pack_bf16x2(f[6], f[7]);
+                        *reinterpret_cast<uint4*>(slice + off) = o;
+                    }
+                }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (elect_one()) {
+                tma_store_2d(&p.tmOut, slice, n0 + c * ecols, m0 + quarter * 32);
+                bulk_commit();
+            }
+        }
+    }
+    if (elect_one()) bulk_wait_read_0();
+    tc_fence_before();
+}
+
 }  // namespace rtod

@@ -74,8 +74,13 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
     uint64_t* res_full = acc_empty + 2;                 // [kEpiWarps][2] TMA (shortcut operand) -> epilogue warp
     uint64_t* wres_bar = res_full + 2 * kEpiWarps;      // [1] resident weights have landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
+    int* s_last = reinterpret_cast<int*>(tmem_slot + 1);       // split-K: this CTA finishes the current tile
 
     const int num_kb = p.ks * p.ks * p.cchunks;
+    // work items: tile, or (tile, K slice) with split-K -- slices of a tile are adjacent items, so they run
+    // concurrently on different CTAs
+    const int n_items = p.total_tiles << p.split_shift;
+    const int kb_per = (num_kb + p.split_k - 1) >> p.split_shift;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.tmA);
@@ -119,7 +124,10 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
             const int cin = p.cchunks * p.BK;
             TRACE_DECL(dbg_wait);
             TRACE_T0(dbg_start);
-            for (int tile = blockIdx.x; ok && tile < p.total_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; ok && item < n_items; item += gridDim.x) {
+                const int tile = item >> p.split_shift;
+                const int kb0 = (item & (p.split_k - 1)) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+                int kb = 0;
                 const int n_tile = (int)fast_div((uint32_t)tile, p.fd_mtiles);
                 const int m0 = (tile - n_tile * p.m_tiles) * kBM;
                 int ow = 0, oh = 0, on = 0;
@@ -133,7 +141,8 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                 // one dependent instruction every ~5 cycles; one integer divide costs ~150)
                 for (int ky = 0; ok && ky < p.ks; ++ky)
                 for (int kx = 0; ok && kx < p.ks; ++kx) {
-                    for (int c0 = 0; c0 < cin; c0 += p.BK) {
+                    for (int c0 = 0; c0 < cin; c0 += p.BK, ++kb) {
+                        if (kb < kb0 || kb >= kb1) continue;         // another CTA's K slice
                         if (skip) {
                             --skip;
                             continue;
@@ -172,10 +181,11 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                 int stage = 0;
                 uint32_t phase = 0;
                 bool ok = true;
-                const int ktot = num_kb * p.BK;
-                for (int tile = blockIdx.x; ok && tile < p.total_tiles; tile += gridDim.x) {
+                for (int item = blockIdx.x; ok && item < n_items; item += gridDim.x) {
+                    const int tile = item >> p.split_shift;
+                    const int kb0 = (item & (p.split_k - 1)) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
                     const int n0 = (int)fast_div((uint32_t)tile, p.fd_mtiles) * p.BN;
-                    for (int k0 = 0; k0 < ktot; k0 += p.BK) {
+                    for (int k0 = kb0 * p.BK; k0 < kb1 * p.BK; k0 += p.BK) {
                         if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag)) { ok = false; break; }
                         mbar_expect_tx(&full_bar[stage], b_bytes);
                         tma_load_2d(smem + (size_t)stage * stage_bytes + a_bytes, &p.tmB, &full_bar[stage], k0, n0);
@@ -201,7 +211,8 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
             TRACE_DECL(dbg_wfull);
             TRACE_T0(dbg_start);
             if (p.b_resident) ok = mbar_wait(wres_bar, 0u, p.err_flag);
-            for (int tile = blockIdx.x; ok && tile < p.total_tiles; tile += gridDim.x, ++local) {
+            for (int item = blockIdx.x; ok && item < n_items; item += gridDim.x, ++local) {
+                const int kb0 = (item & (p.split_k - 1)) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
                 const int buf = local & 1;
                 const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
                 TRACE_T0(w0);
@@ -209,7 +220,7 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                 TRACE_ADD(dbg_wacc, w0);
                 tc_fence_after();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.BN);
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     TRACE_T0(w1);
                     if (!mbar_wait(&full_bar[stage], phase, p.err_flag)) { ok = false; break; }
                     TRACE_ADD(dbg_wfull, w1);
@@ -220,7 +231,7 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                     uint64_t da = desc_tmpl | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
                     uint64_t db = desc_tmpl | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
                     for (int k = 0; k < ksteps; ++k, da += 2, db += 2)      // +32 bytes per K=16 step
-                        umma_bf16(tmem_acc, da, db, p.idesc, (uint32_t)(kb | k));
+                        umma_bf16(tmem_acc, da, db, p.idesc, (uint32_t)((kb - kb0) | k));
                     umma_commit(&empty_bar[stage]);          // frees the stage when the MMAs retire
                     if (++stage == p.stages) {
                         stage = 0;
@@ -237,14 +248,25 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
         }
     } else {
         // ================= epilogue (conv_epilogue.cuh) =================
-        conv_epilogue<kEpiWarps>(
-            p, tmem_base, acc_full, epi_stage, res_full, warp - kFirstEpiWarp, lane, (int)blockIdx.x, (int)gridDim.x,
-            [&](int tile, int& m0, int& n0) {
-                const int n_tile = (int)fast_div((uint32_t)tile, p.fd_mtiles);
-                m0 = (tile - n_tile * p.m_tiles) * kBM;
-                n0 = n_tile * p.BN;
-            },
-            [&](int buf) { mbar_arrive(&acc_empty[buf]); });
+        auto origin = [&](int tile, int& m0, int& n0) {
+            const int n_tile = (int)fast_div((uint32_t)tile, p.fd_mtiles);
+            m0 = (tile - n_tile * p.m_tiles) * kBM;
+            n0 = n_tile * p.BN;
+        };
+        auto release = [&](int buf) { mbar_arrive(&acc_empty[buf]); };
+        if (p.split_k > 1)
+            conv_epilogue_split<kEpiWarps>(
+                p, tmem_base, acc_full, epi_stage, res_full, s_last, warp - kFirstEpiWarp, lane,
+                [&](int local, int& tile, int& slice_k) {
+                    const int item = (int)blockIdx.x + local * (int)gridDim.x;
+                    tile = item >> p.split_shift;
+                    slice_k = item & (p.split_k - 1);
+                    return item < n_items;
+                },
+                origin, release);
+        else
+            conv_epilogue<kEpiWarps>(p, tmem_base, acc_full, epi_stage, res_full, warp - kFirstEpiWarp, lane,
+                                     (int)blockIdx.x, (int)gridDim.x, origin, release);
     }
 
 #ifdef RTOD_TC_TRACE
@@ -262,6 +284,25 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
 }
 
 }  // namespace
+
+// K slices per output tile.  Small batches leave most SMs idle (13x13x1024 at batch 1: two M tiles) behind a
+// long serial k-loop: split K until the narrowest tiling would fill the GPU, keeping >= 8 k-blocks per slice
+// and the fp32 partials inside the plan's scratch.  Depends on the shape only (see conv_tc_prepare).
+int conv_split_factor(const ConvArgs& a) {
+    if (getenv("RTOD_TC_NO_SPLITK") || !a.split_scratch) return 1;
+    const int BK = pick_bk(a.Cin);
+    if (BK == 0) return 1;
+    const long long m_tiles = ((long long)a.B * a.out.H * a.out.W + kBM - 1) / kBM;
+    const long long tiles32 = m_tiles * (a.Cout_pad / 32);
+    const int nkb = a.ks * a.ks * (a.Cin / BK);
+    int split = 1;
+    if (nkb < 64) return 1;                               // measured: the two-pass epilogue only pays for long k-loops
+    while (split < 8 && tiles32 * split < kNumSMs && nkb / (split * 2) >= 8 &&
+           (unsigned long long)m_tiles * kBM * a.Cout_pad * 4ull * (split * 2) <= a.split_scratch_bytes &&
+           m_tiles * (a.Cout_pad / 32) <= a.split_count_n)
+        split *= 2;
+    return split;
+}
 
 bool conv_tc_supported(const ConvArgs& a) {
     if (a.in.fp32 || pick_bk(a.Cin) == 0) return false;
@@ -379,7 +420,23 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
         }
     }
     p.epi_warps = epi_warps;
-    launch->choice = ConvTcChoice{ctas_per_sm, p.b_resident, p.stage_bufs, 0, BN};
+    {   // split-K: a function of the layer shape only (conv_split_factor) -- never of timing -- so that two plans
+        // of the same network always add the partial sums in the same order; tests may force a factor
+        int split = force && force->split > 0 ? force->split : conv_split_factor(a);
+        const int nkb = a.ks * a.ks * (a.Cin / BK);
+        const long long tiles = ((M + kBM - 1) / kBM) * (a.Cout_pad / BN);
+        if (split > 1) {
+            const int per = (nkb + split - 1) / split;
+            if ((split & (split - 1)) || per * (split - 1) >= nkb || !a.split_scratch || tiles > a.split_count_n ||
+                (unsigned long long)tiles * split * kBM * BN * 4ull > a.split_scratch_bytes)
+                return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: split-K %d not applicable", split);
+        }
+        p.split_k = split;
+        p.split_shift = split == 8 ? 3 : (split == 4 ? 2 : (split == 2 ? 1 : 0));
+        p.split_scratch = a.split_scratch;
+        p.split_count = a.split_count;
+    }
+    launch->choice = ConvTcChoice{ctas_per_sm, p.b_resident, p.stage_bufs, 0, BN, p.split_k};
     // im2col issue costs a thread ~350 cycles: two alternating A producers when a k-block's MMAs take less
     p.a_producers = (a.ks > 1 && (BK / 16) * (BN / 2) < 350 && getenv("RTOD_TC_ONE_A") == nullptr) ? 2 : 1;
     {   // channels per epilogue chunk: one 128-byte staging row, narrower if the tile has fewer columns per group
@@ -399,7 +456,10 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
     store_fastdiv(p.fd_wo, (uint32_t)a.out.W);
     store_fastdiv(p.fd_howo, (uint32_t)(a.out.W * a.out.H));
     launch->smem_bytes = stages * stage_bytes_eff + fixed;
-    launch->grid = dim3((unsigned)(p.total_tiles < kNumSMs * ctas_per_sm ? p.total_tiles : kNumSMs * ctas_per_sm), 1, 1);
+    {
+        const int items = p.total_tiles * p.split_k;
+        launch->grid = dim3((unsigned)(items < kNumSMs * ctas_per_sm ? items : kNumSMs * ctas_per_sm), 1, 1);
+    }
 
     // ---- A ----
     const cuuint32_t estr1[4] = {1, 1, 1, 1};
@@ -475,11 +535,12 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
 
 // Plan-bind-time choice among the launch configurations that fit: each candidate is run on the layer's real
 // buffers (contents irrelevant: the kernels' timing does not depend on the data) and the fastest is kept.
-// All candidates accumulate over K in the same order, so the choice does not change the results.
+// All candidates accumulate over K in the same order (the split-K factor is a function of the shape, not a
+// candidate), so the choice does not change the results.
 int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cudaStream_t stream) {
     if (const char* f = getenv("RTOD_TC_FORCE")) {       // tests: "pair,bn,ctas,resident,sbufs" -> exactly that candidate
         ConvTcChoice c{};
-        if (sscanf(f, "%d,%d,%d,%d,%d", &c.pair, &c.bn, &c.ctas, &c.resident, &c.sbufs) == 5 &&
+        if (sscanf(f, "%d,%d,%d,%d,%d,%d", &c.pair, &c.bn, &c.ctas, &c.resident, &c.sbufs, &c.split) >= 5 &&
             conv_tc_prepare(a, err_flag, launch, &c) == RTOD_OK)
             return RTOD_OK;                              // (a candidate that does not fit falls through to the default)
     }
@@ -505,16 +566,16 @@ int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cud
         }
         return RTOD_OK;
     };
-    const int bn_default = launch->patch == 2 ? 256 : launch->choice.bn;
     for (int pair = 1; pair >= 0; --pair)
-      for (int bn = 256; bn >= 64; bn >>= 1)
+      for (int bn = 256; bn >= 32; bn >>= 1)
         for (int ctas = 3; ctas >= 1; --ctas)
             for (int resident = 1; resident >= 0; --resident)
                 for (int sbufs = 2; sbufs >= 1; --sbufs) {
                     if (pair && (bn != 256 || ctas != 1 || resident != 0 || sbufs != 2)) continue;   // one pair configuration
-                    if (!pair && (bn > bn_default || bn > a.Cout_pad)) continue;   // never wider than the heuristic's tile
+                    if (!pair && bn > a.Cout_pad) continue;
                     if (sbufs == 1 && a.res) continue;       // the shortcut operand is prefetched into the 2nd slice
-                    const ConvTcChoice c{ctas, resident, sbufs, pair, bn};
+                  {
+                    const ConvTcChoice c{ctas, resident, sbufs, pair, bn, 0};
                     cand = ConvTcLaunch{};
                     if (conv_tc_prepare(a, err_flag, &cand, &c) != RTOD_OK) continue;      // does not fit / apply
                     float ms;
@@ -523,15 +584,16 @@ int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cud
                         best_ms = ms;
                         best = cand;
                     }
+                  }
                 }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (rc) return rc;
     *launch = best;
     if (getenv("RTOD_TC_TUNE_DBG"))
-        fprintf(stderr, "conv_tc_autotune: M %d Cin %d Cout %d ks %d s %d -> %s BN %d ctas %d resident %d sbufs %d stages %d (%.1f us)\n",
+        fprintf(stderr, "conv_tc_autotune: M %d Cin %d Cout %d ks %d s %d -> %s BN %d ctas %d resident %d sbufs %d split %d stages %d (%.1f us)\n",
                 a.B * a.out.H * a.out.W, a.Cin, a.Cout, a.ks, a.stride, best.patch == 2 ? "pair" : "tc", best.choice.bn, best.choice.ctas,
-                best.choice.resident, best.choice.sbufs, best.p.stages, best_ms * 1e3f);
+                best.choice.resident, best.choice.sbufs, best.choice.split, best.p.stages, best_ms * 1e3f);
     return RTOD_OK;
 }
 

@@ -29,6 +29,9 @@ struct alignas(64) ConvTcParams {
     int tmem_cols;              // 2 * BN rounded up to a power of two
     int m_tiles, total_tiles;   // tile = m_tile + m_tiles * n_tile
     uint32_t idesc;             // tcgen05 instruction descriptor (bf16 x bf16 -> fp32, M=128, N=BN)
+    int split_k, split_shift;   // K slices per output tile (power of two, 1 = off) and log2 of it
+    float* split_scratch;       // [total_tiles][split_k][128][BN] fp32 partial accumulators
+    int* split_count;           // [total_tiles] arrival counters (zero between forwards)
     uint32_t fd_mtiles[3], fd_wo[3], fd_howo[3];   // FastDiv {mul, shift, d} for m_tiles, Wo, Ho*Wo (tc_ptx.cuh)
 };
 
@@ -56,6 +59,7 @@ struct alignas(64) ConvPatchParams {
 struct ConvTcChoice {           // one launch configuration of conv_tc_kernel (or the CTA-pair kernel)
     int ctas, resident, sbufs, pair;
     int bn;                     // N tile (0 = heuristic)
+    int split;                  // K slices per tile (0/1 = no split-K)
 };
 
 struct ConvTcLaunch {           // host side: kernel parameters + launch geometry
@@ -77,6 +81,8 @@ bool conv_patch_eligible(const ConvArgs& a);
 int conv_patch_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch);
 int conv_patch_launch(const ConvTcLaunch& launch, cudaStream_t stream);
 
+// K slices per output tile for this shape (1 = none); deterministic
+int conv_split_factor(const ConvArgs& a);
 // true if the tensor-core kernel tiles this convolution
 bool conv_tc_supported(const ConvArgs& a);
 // fills `p` (encodes the TMA descriptors); `err_flag` is a device int

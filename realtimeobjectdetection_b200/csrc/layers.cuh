@@ -22,6 +22,10 @@ struct ConvArgs {
     int res_pitch;
     int B, Cin, Cout, Cout_pad, ks, stride, pad, leaky;
     int K;                      // ks*ks*Cin
+    float* split_scratch;       // split-K scratch shared by all layers of a plan (or null)
+    size_t split_scratch_bytes;
+    int* split_count;           // zeroed counters, split_count_n entries
+    int split_count_n;
 };
 
 int launch_stem_conv(const float* x_nchw, int B, int Cin, int H, int W, const float* w_f32,

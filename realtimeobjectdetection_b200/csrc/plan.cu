@@ -21,6 +21,8 @@
 namespace rtod {
 
 constexpr size_t kArenaAlign = 1024;
+constexpr size_t kSplitScratchBytes = 8u << 20;   // split-K partial accumulators (small batches only)
+constexpr int kSplitCounters = 16384;
 constexpr int kInputLayer = -1;          // pseudo index of the network input
 
 struct Buf {
@@ -55,6 +57,7 @@ struct RtodPlan {
     unsigned flags = 0;
     int input_buf = -1;                  // NHWC copy of the input when layer 0 is not a stem conv
     size_t workspace_bytes = 0, weight_bytes = 0;
+    size_t split_off = 0;                // offset of the split-K scratch inside the workspace
     unsigned char* ws = nullptr;
     unsigned char* wa = nullptr;
     int* err_flag = nullptr;
@@ -313,7 +316,9 @@ int build(RtodPlan& p) {
         arena = std::max(arena, off + b.bytes);
         placed.push_back(id);
     }
-    p.workspace_bytes = arena;
+    // split-K scratch (fp32 partial tiles) + per-tile arrival counters, shared by all layers (they run in order)
+    p.split_off = align_up(arena, 256);
+    p.workspace_bytes = p.split_off + kSplitScratchBytes + kSplitCounters * sizeof(int);
 
     // ---- weight arena ---------------------------------------------------------------------------
     size_t woff = 0;
@@ -403,6 +408,10 @@ int bind_layers(RtodPlan& p) {
             a.res = reinterpret_cast<const __nv_bfloat16*>(r.ptr);
             a.res_pitch = r.pitch;
         }
+        a.split_scratch = reinterpret_cast<float*>(p.ws + p.split_off);
+        a.split_scratch_bytes = kSplitScratchBytes;
+        a.split_count = reinterpret_cast<int*>(p.ws + p.split_off + kSplitScratchBytes);
+        a.split_count_n = kSplitCounters;
         a.B = p.batch; a.Cin = nd.Cin; a.Cout = nd.d.filters; a.Cout_pad = nd.Cout_pad;
         a.ks = nd.d.size; a.stride = nd.d.stride; a.pad = nd.d.pad; a.leaky = nd.d.leaky; a.K = nd.K;
         nd.use_tc = false;
@@ -442,6 +451,7 @@ extern "C" int rtod_plan_create(const RtodLayerDesc* layers, int n_layers, int b
 
 extern "C" void rtod_plan_destroy(RtodPlan* plan) { delete plan; }
 extern "C" size_t rtod_plan_workspace_bytes(const RtodPlan* p) { return p ? p->workspace_bytes : 0; }
+extern "C" size_t rtod_plan_scratch_bytes(const RtodPlan* p) { return p ? p->workspace_bytes - p->split_off : 0; }
 extern "C" size_t rtod_plan_weight_bytes(const RtodPlan* p) { return p ? p->weight_bytes : 0; }
 extern "C" int rtod_plan_num_rows(const RtodPlan* p) { return p ? p->n_rows : 0; }
 extern "C" int rtod_plan_num_attrs(const RtodPlan* p) { return p ? p->n_attrs : 0; }
@@ -471,6 +481,7 @@ extern "C" int rtod_plan_bind(RtodPlan* p, void* workspace, size_t workspace_byt
     // padded weight rows / bias entries must read as zero
     RTOD_CUDA_OK(cudaMemset(p->wa, 0, p->weight_bytes));
     RTOD_CUDA_OK(cudaMemset(p->ws, 0, kArenaAlign));
+    RTOD_CUDA_OK(cudaMemset(p->ws + p->split_off + kSplitScratchBytes, 0, kSplitCounters * sizeof(int)));
     RTOD_CUDA_OK(cudaDeviceSynchronize());         // bind is rare; later work may use any stream
     for (Node& nd : p->nodes) nd.weights_set = false;
     const int rc = bind_layers(*p);

@@ -305,6 +305,43 @@ def test_conv_block_every_launch_configuration(lib, monkeypatch, cin, cout, k, s
     monkeypatch.delenv("RTOD_TC_FORCE")
 
 
+@pytest.mark.parametrize("cin,cout,k,stride,H,batch", [(512, 1024, 3, 1, 13, 1), (256, 512, 3, 1, 26, 1),
+                                                       (1024, 512, 1, 1, 13, 2), (128, 256, 3, 2, 52, 1)])
+@pytest.mark.parametrize("split", [2, 4, 8])
+def test_conv_block_split_k(lib, monkeypatch, cin, cout, k, stride, H, batch, split):
+    """small batches: K split over several CTAs per tile, partials summed in slice order by the last arriver;
+    run twice (the arrival counters must be back at zero) and with a shortcut operand"""
+    rng = np.random.RandomState(cin + cout + k + split)
+    x = torch.from_numpy(rng.randn(batch, cin, H, H).astype(np.float32))
+    w = rand_conv(rng, cin, cout, k)
+    ref_q = ref_block(x, w, k, stride, True, True)
+    monkeypatch.setenv("RTOD_TC_FORCE", "0,32,2,0,2,%d" % split)
+    got = run_block(lib, [conv_desc(cout, k, stride)], x, {0: w})[0]
+    assert frac_within(got, ref_q) >= 0.9999
+    monkeypatch.setenv("RTOD_TC_FORCE", "0,64,1,0,2,%d" % split)
+    got2 = run_block(lib, [conv_desc(cout, k, stride)], x, {0: w})[0]
+    assert frac_within(got2, ref_q) >= 0.9999
+    monkeypatch.delenv("RTOD_TC_FORCE")
+
+
+def test_residual_block_split_k(lib, monkeypatch):
+    rng = np.random.RandomState(29)
+    x = torch.from_numpy(rng.randn(1, 512, 13, 13).astype(np.float32))
+    w0, w1, w2 = rand_conv(rng, 512, 1024, 3), rand_conv(rng, 1024, 512, 1), rand_conv(rng, 512, 1024, 3)
+    sc = _lib.RtodLayerDesc()
+    sc.type, sc.src0, sc.src1 = _lib.LAYER_SHORTCUT, 2, 0
+    monkeypatch.setenv("RTOD_TC_FORCE", "0,32,2,0,2,4")
+    outs = run_block(lib, [conv_desc(1024, 3, 1), conv_desc(512, 1, 1), conv_desc(1024, 3, 1), sc], x,
+                     {0: w0, 1: w1, 2: w2})
+    monkeypatch.delenv("RTOD_TC_FORCE")
+    y0 = ref_block(x, w0, 3, 1, True, True).bfloat16().float()
+    y1 = ref_block(y0, w1, 1, 1, True, True).bfloat16().float()
+    y3 = ref_block(y1, w2, 3, 1, True, True) + y0
+    assert frac_within(outs[0], y0) >= 0.9999
+    assert frac_within(outs[3], y3) >= 0.999
+    assert torch.equal(outs[2], outs[3])
+
+
 def test_conv_head_keeps_fp32_logits(lib):
     """A convolution that only feeds a yolo layer stores fp32 (255 channels, no activation) and the
     single decode launch turns it into prediction rows."""
