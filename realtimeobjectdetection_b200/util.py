@@ -123,13 +123,19 @@ class PendingDetections:
     def __init__(self, rows, count_host, event, home, cap, device):
         self._rows, self._count_host, self._event = rows, count_host, event
         self._home, self._cap, self._device = home, cap, device
+        self._d = None
 
     def result(self, to_host: bool = False):
         """``[D, 8]`` rows or the int ``0`` (the reference's convention).  Waits only for the event recorded
         after this call's kernels -- work enqueued later on the stream (the next batch) keeps running.
         ``to_host``: copy the rows to the host on a side stream instead of the compute stream."""
-        self._event.synchronize()
-        d = int(self._count_host[0])
+        if self._count_host is not None:
+            self._event.synchronize()
+            self._d = int(self._count_host[0])
+            if len(_PINNED_COUNTS) < 64:
+                _PINNED_COUNTS.append(self._count_host)        # recycled: no host allocation per call
+            self._count_host = None
+        d = self._d
         if d == 0:
             return 0
         if d > self._cap:
@@ -145,6 +151,7 @@ class PendingDetections:
 
 
 _SIDE_STREAMS = {}
+_PINNED_COUNTS = []                                     # recycled 1-element pinned int32 tensors
 
 
 def _side_stream(device):
@@ -168,7 +175,7 @@ def write_results_async(prediction, num_class, confidence=0.6, nms_conf=0.4) -> 
     cap = max(B * N, 1)
     rows = torch.empty(cap, 8, dtype=torch.float32, device=dev)
     count = torch.zeros(1, dtype=torch.int32, device=dev)
-    count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    count_host = _PINNED_COUNTS.pop() if _PINNED_COUNTS else torch.zeros(1, dtype=torch.int32).pin_memory()
     event = torch.cuda.Event()
     if B > 0 and N > 0:
         nbytes = lib.rtod_write_results_workspace_bytes(B, N, C)
