@@ -81,6 +81,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (p.pf_bytes && warp == 2 && elect_one()) {
+        // small batches stream every weight from HBM once per forward and the k-loops are latency-bound: pull
+        // the NEXT layer's weights into L2 now (they do not depend on the previous layer, so before the wait)
+        const unsigned long long per = ((p.pf_bytes + gridDim.x - 1) / gridDim.x + 127ull) & ~127ull;
+        const unsigned long long off = per * blockIdx.x;
+        if (off < p.pf_bytes) {
+            unsigned long long left = p.pf_bytes - off < per ? p.pf_bytes - off : per;
+            const char* ptr = static_cast<const char*>(p.pf_ptr) + off;
+            while (left) {
+                const uint32_t n = left > 32768ull ? 32768u : (uint32_t)left;
+                bulk_prefetch_l2(ptr, n);
+                ptr += n;
+                left -= n;
+            }
+        }
+    }
     pdl_wait();                          // everything above overlapped the previous layer's tail
     pdl_launch_dependents();
 

@@ -75,6 +75,16 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
     uint64_t* wres_bar = res_full + 2 * kEpiWarps;      // [1] resident weights have landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
     int* s_last = reinterpret_cast<int*>(tmem_slot + 1);       // split-K: this CTA finishes the current tile
+#ifdef RTOD_TC_TRACE
+    unsigned long long* s_ts = reinterpret_cast<unsigned long long*>(tmem_slot + 4);   // [0] = entry, [1..7] stamps
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) s_ts[i] = 0;
+        s_ts[0] = global_timer_ns();
+    }
+#define TRACE_STAMP(slot) s_ts[slot] = global_timer_ns()
+#else
+#define TRACE_STAMP(slot)
+#endif
 
     const int num_kb = p.ks * p.ks * p.cchunks;
     // work items: tile, or (tile, K slice) with split-K -- slices of a tile are adjacent items, so they run
@@ -106,8 +116,26 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) { TRACE_STAMP(1); }
+    if (p.pf_bytes && warp == 2 && elect_one()) {
+        // small batches stream every weight from HBM once per forward and the k-loops are latency-bound: pull
+        // the NEXT layer's weights into L2 now (they do not depend on the previous layer, so before the wait)
+        const unsigned long long per = ((p.pf_bytes + gridDim.x - 1) / gridDim.x + 127ull) & ~127ull;
+        const unsigned long long off = per * blockIdx.x;
+        if (off < p.pf_bytes) {
+            unsigned long long left = p.pf_bytes - off < per ? p.pf_bytes - off : per;
+            const char* ptr = static_cast<const char*>(p.pf_ptr) + off;
+            while (left) {
+                const uint32_t n = left > 32768ull ? 32768u : (uint32_t)left;
+                bulk_prefetch_l2(ptr, n);
+                ptr += n;
+                left -= n;
+            }
+        }
+    }
     pdl_wait();                          // everything above overlapped the previous layer's tail
     pdl_launch_dependents();
+    if (threadIdx.x == 0) { TRACE_STAMP(2); }
 
     if (warp == 0 || warp == 3) {
         // ================= TMA producer A: activations (im2col gather or [M, Cin] tiles) =================
@@ -165,7 +193,7 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                 }
             }
 #ifdef RTOD_TC_TRACE
-            if ((p.dbg & 8) && blockIdx.x == 0)
+            if ((p.dbg & 16) && blockIdx.x == 0)
                 printf("  tc producer %d: total %lld clk, waiting for empty %lld, tiles %d x %d k-blocks, stages %d, grid %d\n", me,
                        clock64() - dbg_start, dbg_wait, (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x, num_kb, p.stages, (int)gridDim.x);
 #endif
@@ -224,6 +252,7 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                     TRACE_T0(w1);
                     if (!mbar_wait(&full_bar[stage], phase, p.err_flag)) { ok = false; break; }
                     TRACE_ADD(dbg_wfull, w1);
+                    if (local == 0 && kb == kb0) { TRACE_STAMP(3); }
                     tc_fence_after();
                     // descriptors differ from the template only in the 14-bit start-address field
                     const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
@@ -239,9 +268,11 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                     }
                 }
                 umma_commit(&acc_full[buf]);                 // accumulator of this tile complete
+                if (local == 0) { TRACE_STAMP(4); }
             }
+            TRACE_STAMP(5);
 #ifdef RTOD_TC_TRACE
-            if ((p.dbg & 8) && blockIdx.x == 0)
+            if ((p.dbg & 16) && blockIdx.x == 0)
                 printf("  tc mma: total %lld clk, waiting for full %lld, for acc_empty %lld (BN %d BK %d resident %d epi_warps %d)\n",
                        clock64() - dbg_start, dbg_wfull, dbg_wacc, p.BN, p.BK, p.b_resident, p.epi_warps);
 #endif
@@ -269,14 +300,18 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                                      (int)blockIdx.x, (int)gridDim.x, origin, release);
     }
 
+    if (warp == kFirstEpiWarp && lane == 0) { TRACE_STAMP(6); }
+    __syncthreads();
 #ifdef RTOD_TC_TRACE
     if ((p.dbg & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
         const long long dc = clock64() - dbg_c0;
         const unsigned long long dt = global_timer_ns() - dbg_t0;
         printf("%s M %d Cout %d ks %d: %lld clk in %llu ns = %.0f MHz\n", "conv_tc", p.M, p.Cout, p.ks, dc, dt, (double)dc * 1e3 / (double)dt);
+        printf("    ns since entry: prologue %llu | prev layer done %llu | first operands %llu | first tile MMAs issued %llu | MMA done %llu | epilogue done %llu | exit %llu\n",
+               s_ts[1] - s_ts[0], s_ts[2] - s_ts[0], s_ts[3] - s_ts[0], s_ts[4] - s_ts[0], s_ts[5] - s_ts[0], s_ts[6] - s_ts[0],
+               global_timer_ns() - s_ts[0]);
     }
 #endif
-    __syncthreads();
     if (warp == kFirstEpiWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);

@@ -29,6 +29,8 @@ struct alignas(64) ConvTcParams {
     int tmem_cols;              // 2 * BN rounded up to a power of two
     int m_tiles, total_tiles;   // tile = m_tile + m_tiles * n_tile
     uint32_t idesc;             // tcgen05 instruction descriptor (bf16 x bf16 -> fp32, M=128, N=BN)
+    const void* pf_ptr;         // next convolution's weights: prefetched into L2 while this layer runs (small batches)
+    unsigned long long pf_bytes;
     int split_k, split_shift;   // K slices per output tile (power of two, 1 = off) and log2 of it
     float* split_scratch;       // [total_tiles][split_k][128][BN] fp32 partial accumulators
     int* split_count;           // [total_tiles] arrival counters (zero between forwards)

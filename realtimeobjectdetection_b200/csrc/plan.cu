@@ -14,6 +14,8 @@
 #include <new>
 #include <vector>
 
+#include <cstdlib>
+
 #include "conv_tc.cuh"
 #include "decode.cuh"
 #include "layers.cuh"
@@ -420,6 +422,19 @@ int bind_layers(RtodPlan& p) {
                                                              : conv_tc_autotune(a, p.err_flag, &nd.tc, nullptr);
             if (rc) return rc;
             nd.use_tc = true;
+        }
+    }
+    // small batches: every tcgen05 convolution prefetches the next one's weights into L2 (conv_tc.cu)
+    if ((long long)p.batch * p.in_h * p.in_w <= 4ll * 416 * 416 && getenv("RTOD_NO_WEIGHT_PREFETCH") == nullptr) {
+        Node* prev = nullptr;
+        for (int i = 0; i < n; ++i) {
+            Node& nd = p.nodes[i];
+            if (nd.d.type != RTOD_LAYER_CONV || nd.alias_of >= -1 || !nd.use_tc) continue;
+            if (prev) {
+                prev->tc.p.pf_ptr = p.wa + nd.w_off;
+                prev->tc.p.pf_bytes = (unsigned long long)nd.Cout_pad * nd.K * 2ull;     // multiple of 16
+            }
+            prev = &nd;
         }
     }
     return RTOD_OK;

@@ -103,6 +103,10 @@ static __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUten
         "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
         : "memory");
 }
+// fire-and-forget L2 prefetch of a contiguous range (16-byte aligned, size a multiple of 16)
+static __device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 static __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
                  "r"(smem_u32(src)), "r"(c0), "r"(c1)
