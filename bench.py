@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cfg", default="yolov3")
+    ap.add_argument("--reso", type=int, default=416, help="input size (BASELINE configs[2]: 608); default: the metric's 416")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     return ap.parse_args()
@@ -171,7 +172,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": statistics.median(times) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "yolov3.cfg 416x416, 80 classes, conf 0.5 / nms 0.4, CPU (CUDA=False), "
+        "config": {"workload": "yolov3.cfg %dx%d, 80 classes, conf 0.5 / nms 0.4, CPU (CUDA=False), " % (RESO, RESO) +
                                "batch 1 per call as detect.py:27, %d frames per step" % frames_per_step,
                    "weights": "synthetic calibrated seed 0", "bn": "eval (running statistics)"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
@@ -334,7 +335,7 @@ def run_b200(args):
                 # dram__bytes_read + dram__bytes_write of one captured conv_pair_kernel launch (13x13 3x3 512->1024
                 # layer at B=64, ncu --set full: 42.70 MB read + 1.33 MB written before the kernel ends; the output
                 # stays in L2); its algorithmic bytes (in + weights + out, bf16) are 42.6 MB
-                "traffic": 44.0e6 if (args.cfg == "yolov3" and B == 64) else None,
+                "traffic": 44.0e6 if (args.cfg == "yolov3" and B == 64 and RESO == 416) else None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s): kernel timed inside a long step"
                                % peaks["source"],
                 "launches_per_step": n_tc, "flops_per_step": tc_flops / reps,
@@ -413,7 +414,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "yolov3.cfg 416x416 forward+decode+NMS, 80 classes, conf 0.5 / nms 0.4, "
+            "config": {"workload": "yolov3.cfg %dx%d forward+decode+NMS, 80 classes, conf 0.5 / nms 0.4, " % (RESO, RESO) +
                                    "batch %d per GPU" % B,
                        "global_batch": world * B, "parallelism": "frames sharded, dp%d, no collective on the hot "
                                                                  "path; detections gathered to rank 0" % world,
@@ -434,6 +435,9 @@ def run_b200(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    RESO = a.reso
+    if RESO != 416:
+        METRIC = "YOLOv3-%d frames/s (fwd+decode+NMS)" % RESO
     # libraries (NCCL's version banner) write to stdout: keep fd 1 for the one JSON line
     _real_stdout = os.dup(1)
     os.dup2(2, 1)
