@@ -267,6 +267,25 @@ def run_b200(args):
     clocks = sampler.stop(t0, t1)
     value = world * B * K / (ms_total / 1e3)
     model.check_device()
+    # nvidia-smi gets only a handful of samples inside a ~0.1 s timed region: a second, UNTIMED pass of the same
+    # steps with a one-thread kernel counting SM cycles per 0.5 ms of wall time on a side stream
+    # (rtod_sm_clock_probe; it slows the step down, which is why it is not part of the timed region)
+    try:
+        side = torch.cuda.Stream(dev)
+        n_win = max(8, int(K * (ms_total / K) / 0.5))
+        mhz = torch.zeros(n_win, device=dev)
+        torch.cuda.synchronize()
+        _lib.check(lib.rtod_sm_clock_probe(mhz.data_ptr(), n_win, 500, side.cuda_stream))
+        for i in range(K + 2):
+            step(i)
+        collect()
+        torch.cuda.synchronize()
+        vals = sorted(float(v) for v in mhz.cpu() if v > 0)
+        if vals:
+            clocks["sm_mhz_in_kernel"] = {"median": vals[len(vals) // 2], "min": vals[0], "max": vals[-1],
+                                          "windows": len(vals), "how": "clock64 / globaltimer per 0.5 ms, untimed pass"}
+    except Exception as exc:                      # measurement aid only
+        clocks["sm_mhz_in_kernel"] = {"error": str(exc)}
 
     # ---- e2e: host buffers, H2D inside the timed region, detections read back ------------------
     host = [torch.rand(B, 3, RESO, RESO).pin_memory() for _ in range(2)]
