@@ -13,8 +13,11 @@
 //   * tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN<=256, K=16) accumulates in TMEM; one
 //     elected thread issues, tcgen05.commit releases shared-memory stages back to the TMA
 //     producer through mbarriers and publishes each finished accumulator to the epilogue.
-//   * persistent CTAs (one per SM) loop over output tiles; the accumulator is double-buffered in
-//     TMEM (2 x BN columns) so the epilogue of one tile overlaps the MMAs of the next.
+//   * persistent CTAs (1-3 per SM) loop over output tiles; the accumulator is double-buffered in
+//     TMEM (2 x BN columns) so the epilogue of one tile overlaps the MMAs of the next.  Small
+//     batches: K is split over several CTAs per tile (conv_epilogue_split) and the next layer's
+//     weights are prefetched into L2.  Layers with Cout % 256 == 0 and enough tiles run on CTA pairs
+//     instead (conv_pair.cu); conv_tc_autotune picks the configuration per layer at bind time.
 //   * four or eight epilogue warps (conv_epilogue.cuh), each an independent pipeline over its 32
 //     rows of the tile: tcgen05.ld (32 lanes x 32 columns), folded bias, leaky 0.1, shortcut operand
 //     (TMA-loaded one chunk ahead into the warp's own staging slice), bf16 (or the fp32 logits of a
@@ -23,8 +26,9 @@
 //     channels beyond Cout are clipped by the descriptor.
 //
 // Warp roles (128 + 32*kEpiWarps threads): warp 0 = TMA producer A, warp 1 = MMA issuer, warp 2 = TMA
-// producer B, warp 3 = second producer A (thin tiles), warps 4.. = epilogue (warp 4 owns the TMEM allocation).  Every mbarrier wait is bounded: on a time-out
-// the kernel raises *err_flag and drains instead of hanging the GPU.
+// producer B, warp 3 = second producer A (thin tiles), warps 4.. = epilogue (warp 4 owns the TMEM
+// allocation).  All TMA / tcgen05 instructions are issued from elect.sync regions.  Every mbarrier
+// wait is bounded: on a time-out the kernel raises *err_flag and drains instead of hanging the GPU.
 #include "conv_epilogue.cuh"
 #include "conv_tc.cuh"
 #include "tc_ptx.cuh"
