@@ -15,13 +15,17 @@ from .util import write_results_async
 
 class DetectionPipeline:
     def __init__(self, model, num_class: int, confidence: float = 0.6, nms_conf: float = 0.4,
-                 device=None, depth: int = 2):
+                 device=None, depth: int = 2, collect_lag: int = 1):
         if not torch.cuda.is_available():
             raise RuntimeError("DetectionPipeline needs a CUDA device; there is no CPU fallback")
         self.model, self.num_class = model, int(num_class)
         self.confidence, self.nms_conf = float(confidence), float(nms_conf)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.depth = max(2, int(depth))
+        # 1 (throughput): a batch's detections are awaited after the NEXT batch is in the stream, the GPU never
+        # idles on the host.  0 (live video, per-frame latency): every batch is collected before the next frame
+        # is requested from the source.
+        self.collect_lag = 1 if collect_lag else 0
         self.copy_stream = torch.cuda.Stream(self.device)
         self._slots = []
         self.h2d_bytes = 0
@@ -69,10 +73,13 @@ class DetectionPipeline:
             pred = self.model(pending["buf"])
             handle = write_results_async(pred, self.num_class, self.confidence, self.nms_conf)
             pending["free"].record(compute)
-            # this batch is in the stream: only now wait for the previous one (the GPU keeps working)
-            if prev is not None:
-                yield self._collect(prev)
-            prev = handle
+            if self.collect_lag == 0:
+                yield self._collect(handle)
+            else:
+                # this batch is in the stream: only now wait for the previous one (the GPU keeps working)
+                if prev is not None:
+                    yield self._collect(prev)
+                prev = handle
             pending, k = nxt, k + 1
         if prev is not None:
             yield self._collect(prev)

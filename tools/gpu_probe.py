@@ -253,6 +253,38 @@ def stage_ncufwd():
     print("profiled one forward + write_results, B=%d, %d detections" % (batch, 0 if isinstance(det, int) else len(det)))
 
 
+def stage_stream():
+    """BASELINE configs[4]: YOLOv3-tiny 320x320 streaming, batch 1, pinned frames, async H2D on a side stream:
+    per-frame latency (frame handed over -> detections on the host) and sustained frames/s"""
+    from realtimeobjectdetection_b200.pipeline import DetectionPipeline
+    cfg, blocks, stream, state = make_network("yolov3-tiny", 3, "calibrated")
+    model = Darknet(cfg, True)
+    model.load_state_dict({**model.state_dict(), **state})
+    model.net_info["height"] = 320
+    model.eval()
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+    frames = [(torch.randint(0, 256, (1, 3, 320, 320), dtype=torch.uint8).float() / 255.0).pin_memory() for _ in range(8)]
+    for lag in (0, 1):
+        pipe = DetectionPipeline(model, 80, 0.5, 0.4, collect_lag=lag)
+        for _ in pipe.run(frames[i & 7] for i in range(50)):
+            pass
+        torch.cuda.synchronize()
+        stamps = []
+
+        def source():
+            for i in range(n):
+                stamps.append(time.perf_counter())
+                yield frames[i & 7]
+        lat = []
+        t0 = time.perf_counter()
+        for k, det in enumerate(pipe.run(source())):
+            lat.append(time.perf_counter() - stamps[k])
+        total = time.perf_counter() - t0
+        lat = np.sort(np.array(lat)) * 1e3
+        print("tiny-320 streaming B=1 collect_lag=%d: %.0f frames/s, per-frame latency p50 %.3f ms p99 %.3f ms" %
+              (lag, n / total, lat[len(lat) // 2], lat[int(len(lat) * 0.99)]))
+
+
 def stage_nmsbench():
     """BASELINE configs[3]: write_results on [256, 10647, 85] at 1/10/50 % density, C-ABI call only
     (CUDA events), plus the decode microbench on [256, 255, G, G] heads."""
