@@ -12,6 +12,8 @@
 //
 // Exact op order of the reference: cx = (sigmoid(tx) + x) * stride;
 // w = (exp(tw) * f32(anchor_w / stride)) * stride; sigmoid on objectness and classes.
+#include <cstdlib>
+
 #include "decode.cuh"
 
 namespace rtod {
@@ -141,7 +143,7 @@ yolo_decode_heads_kernel(DecodeHeads heads, int B, int N, int L, int train, int 
 // attributes (attr < 4) depends on the lane only, so the plain-sigmoid elements (249 of 255) run a short
 // uniform path -- exp(-v), 1 + t, correctly rounded reciprocal -- and the twelve special ones take the general
 // formula in the three iterations where they occur.  32-bit index arithmetic (B * cells < 2^31).
-template <bool kTrain>
+template <bool kTrain, bool kExact, bool kYolo>
 __global__ void __launch_bounds__(256)
 yolo_decode_heads_fast_kernel(DecodeHeads heads, unsigned total, int N, int L, unsigned cells_per_image,
                               float* __restrict__ pred) {
@@ -157,6 +159,7 @@ yolo_decode_heads_fast_kernel(DecodeHeads heads, unsigned total, int N, int L, u
             if (e % L < 4) special |= 1u << i;
         }
     }
+    const unsigned plain = valid & ~special;
     // every warp owns a contiguous run of cells: image, head and cell coordinates are located once (two
     // integer divides) and then advanced by additions; a new head or image re-locates
     const unsigned wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -190,25 +193,34 @@ yolo_decode_heads_fast_kernel(DecodeHeads heads, unsigned total, int N, int L, u
             src = heads.raw[h] + ((size_t)b * G * G + cell) * pitch + lane;
             dst = pred + ((size_t)b * N + heads.row_base[h] + (size_t)cell * A) * L + lane;
         }
+        // main pass: every element that is not a box attribute is a plain sigmoid -- one uniform instruction
+        // stream for the whole warp (`plain` = valid & ~special decides the store only)
         float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = (valid >> i) & 1u ? __ldcs(src + 32 * i) : 0.0f;   // read once: streaming
+        for (int i = 0; i < 8; ++i) {
+            // kYolo (3 anchors x 85 attributes): groups 0-6 are complete, only lane 31 of group 7 is missing
+            if (kYolo && i < 7) v[i] = __ldcs(src + 32 * i);                        // read once: streaming
+            else v[i] = (valid >> i) & 1u ? __ldcs(src + 32 * i) : 0.0f;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
+            const float r = kExact ? sigmoid_f32(v[i]) : sigmoid_fast_f32(v[i]);
+            // kYolo: box attributes sit in groups 0 (0-3), 2 (85-88) and 5 (170-173) only
+            if (kYolo && (i == 1 || i == 3 || i == 4 || i == 6)) __stcs(dst + 32 * i, r);
+            else if ((plain >> i) & 1u) __stcs(dst + 32 * i, r);
+        }
+        // fix-up pass: the 4 box attributes of each anchor (A * 4 elements per cell), one lane each
+        if (lane < 4 * A) {
+            const int a = lane >> 2, attr = lane & 3, e = a * L + attr;
+            const float x = __ldg(src - lane + e);           // (src / dst carry the + lane offset)
             float r;
-            if ((special >> i) & 1u) {
-                const int e = lane + 32 * i, a = e / L, attr = e - a * L;
-                if (attr < 2) {
-                    r = sigmoid_f32(v[i]);
-                    if (!kTrain) r = __fmul_rn(__fadd_rn(r, (float)(attr == 0 ? cx : cy)), stride);
-                } else {
-                    r = kTrain ? v[i]
-                               : __fmul_rn(__fmul_rn(expf(v[i]), attr == 2 ? heads.anchor_w[h][a] : heads.anchor_h[h][a]), stride);
-                }
+            if (attr < 2) {
+                r = sigmoid_f32(x);
+                if (!kTrain) r = __fmul_rn(__fadd_rn(r, (float)(attr == 0 ? cx : cy)), stride);
             } else {
-                r = sigmoid_f32(v[i]);
+                r = kTrain ? x : __fmul_rn(__fmul_rn(expf(x), attr == 2 ? heads.anchor_w[h][a] : heads.anchor_h[h][a]), stride);
             }
-            if ((valid >> i) & 1u) __stcs(dst + 32 * i, r);
+            __stcs(dst - lane + e, r);
         }
         src += pitch;
         dst += n;
@@ -230,12 +242,21 @@ int launch_decode_heads(const DecodeHeads& heads, int B, int N, int L, int train
     if (total == 0 || N == 0) return RTOD_OK;
     long long blocks = (total + 7) / 8;
     if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
-    bool fast = total < (1ll << 31) && heads.num_anchors[0] * L <= 256;
+    bool fast = total < (1ll << 31) && heads.num_anchors[0] * L <= 256 && heads.num_anchors[0] <= 8 && L >= 4;
     for (int h = 1; h < heads.count; ++h) fast = fast && heads.num_anchors[h] == heads.num_anchors[0];
-    if (fast && train)
-        yolo_decode_heads_fast_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(heads, (unsigned)total, N, L, (unsigned)cells, pred);
+    static const bool exact = getenv("RTOD_DECODE_EXACT") != nullptr;    // full-precision expf for every element
+    const bool yolo = fast && heads.num_anchors[0] == 3 && L == 85;
+    const unsigned nb = (unsigned)blocks, tot = (unsigned)total, cpi = (unsigned)cells;
+    if (fast && train && exact)
+        yolo_decode_heads_fast_kernel<true, true, false><<<nb, 256, 0, stream>>>(heads, tot, N, L, cpi, pred);
+    else if (fast && train)                              // same sigmoid as the inference decode: TRAIN only changes the box attributes
+        yolo_decode_heads_fast_kernel<true, false, false><<<nb, 256, 0, stream>>>(heads, tot, N, L, cpi, pred);
+    else if (fast && exact)
+        yolo_decode_heads_fast_kernel<false, true, false><<<nb, 256, 0, stream>>>(heads, tot, N, L, cpi, pred);
+    else if (yolo)
+        yolo_decode_heads_fast_kernel<false, false, true><<<nb, 256, 0, stream>>>(heads, tot, N, L, cpi, pred);
     else if (fast)
-        yolo_decode_heads_fast_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(heads, (unsigned)total, N, L, (unsigned)cells, pred);
+        yolo_decode_heads_fast_kernel<false, false, false><<<nb, 256, 0, stream>>>(heads, tot, N, L, cpi, pred);
     else
         yolo_decode_heads_kernel<<<(unsigned)blocks, 256, 0, stream>>>(heads, B, N, L, train, cells, pred);
     RTOD_LAUNCH_OK("yolo_decode_heads_kernel");
