@@ -36,7 +36,7 @@ constexpr int kTileCells = 32;
 constexpr int kTileCh = 256;
 
 __global__ void __launch_bounds__(256)
-yolo_decode_nchw_kernel(const float* __restrict__ head, int G, int A, int L, float stride, int train,
+yolo_decode_nchw_kernel(const float* __restrict__ head, int G, int A, int L, float stride, int train, int exact,
                         DecodeAnchors anchors, float* __restrict__ out) {
     __shared__ float tile[kTileCh][kTileCells + 1];
     const int GG = G * G, Ch = A * L;
@@ -48,31 +48,37 @@ yolo_decode_nchw_kernel(const float* __restrict__ head, int G, int A, int L, flo
         tile[ch][cl] = cl < n_cell ? src[(long long)ch * GG + cl] : 0.0f;
     }
     __syncthreads();
-    // one warp per cell: its channels are contiguous in the output, (anchor, attribute) advance by additions
+    // one warp per cell: its channels are contiguous in the output.  Main pass: every element that is not a box
+    // attribute is a plain sigmoid (one uniform instruction stream); fix-up pass: the 4 box attributes of each
+    // anchor, one lane each, in the reference's op order (same scheme as yolo_decode_heads_fast_kernel)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int step_a = 32 / L, step_attr = 32 - step_a * L;
+    unsigned plain = 0;
+#pragma unroll
+    for (int i = 0; i < kTileCh / 32; ++i) {
+        const int chl = lane + 32 * i;
+        if (chl < n_ch && (ch0 + chl) % L >= 4) plain |= 1u << i;
+    }
     for (int cl = warp; cl < n_cell; cl += 8) {
         const int cell = cell0 + cl;
-        const int cx = cell % G, cy = cell / G;
-        int a = (ch0 + lane) / L, attr = (ch0 + lane) - a * L;
+        const int cy = cell / G, cx = cell - cy * G;
         float* dst = out + ((long long)b * GG + cell) * Ch + ch0;
-        for (int chl = lane; chl < n_ch; chl += 32) {
-            const float v = tile[chl][cl];
-            float r;
-            if (attr >= 4) {
-                r = sigmoid_f32(v);
-            } else if (attr < 2) {
-                r = sigmoid_f32(v);
-                if (!train) r = __fmul_rn(__fadd_rn(r, (float)(attr == 0 ? cx : cy)), stride);
-            } else {
-                r = train ? v : __fmul_rn(__fmul_rn(expf(v), attr == 2 ? anchors.w[a] : anchors.h[a]), stride);
-            }
-            dst[chl] = r;
-            a += step_a;
-            attr += step_attr;
-            if (attr >= L) {
-                attr -= L;
-                ++a;
+#pragma unroll
+        for (int i = 0; i < kTileCh / 32; ++i) {
+            const float r = exact ? sigmoid_f32(tile[lane + 32 * i][cl]) : sigmoid_fast_f32(tile[lane + 32 * i][cl]);
+            if ((plain >> i) & 1u) __stcs(dst + lane + 32 * i, r);
+        }
+        if (lane < 4 * A) {
+            const int a = lane >> 2, attr = lane & 3, chl = a * L + attr - ch0;
+            if (chl >= 0 && chl < n_ch) {
+                const float v = tile[chl][cl];
+                float r;
+                if (attr < 2) {
+                    r = sigmoid_f32(v);
+                    if (!train) r = __fmul_rn(__fadd_rn(r, (float)(attr == 0 ? cx : cy)), stride);
+                } else {
+                    r = train ? v : __fmul_rn(__fmul_rn(expf(v), attr == 2 ? anchors.w[a] : anchors.h[a]), stride);
+                }
+                __stcs(dst + chl, r);
             }
         }
     }
@@ -286,8 +292,10 @@ extern "C" int rtod_yolo_decode(const float* head_nchw, int B, int G, int A, int
     }
     const int L = 5 + C, Ch = A * L, GG = G * G;
     dim3 grid(ceil_div(GG, kTileCells), B, ceil_div(Ch, kTileCh));
+    if (A > 8 || L < 4) return fail(RTOD_ERR_UNSUPPORTED, "rtod_yolo_decode: at most 8 anchors per head");
+    static const int exact = getenv("RTOD_DECODE_EXACT") != nullptr;      // full-precision expf for every element
     yolo_decode_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(head_nchw, G, A, L, (float)stride,
-                                                                    train, anc, out);
+                                                                    train, exact, anc, out);
     RTOD_LAUNCH_OK("yolo_decode_nchw_kernel");
     return RTOD_OK;
 }
