@@ -218,26 +218,37 @@ nms_scan_kernel(const float* __restrict__ pred, long long total_rows, int N, int
         const unsigned long long kmask =
             (unsigned long long)keep_words[0] | ((unsigned long long)keep_words[1] << 32);
 
-        // (b) the i-th surviving row goes to warp i % 8: first-max class, key, append
-        int ordinal = 0;
-        for (unsigned long long rest = kmask; rest; rest &= rest - 1, ++ordinal) {
-            if ((ordinal & 7) != warp) continue;
-            const int r = __ffsll((long long)rest) - 1;
+        // (b) surviving rows, four at a time per warp (8 lanes each): survivor i belongs to warp (i / 4) % 8,
+        //     lane group i % 4.  First-max class over the C scores (ties -> lowest index, NaN as torch.max),
+        //     64-bit sort key, append to the image's candidate list
+        const int n_keep = __popcll(kmask);
+        const int sub = lane >> 3, l8 = lane & 7;
+        const int row_a0 = (int)(first - img_a * (long long)N);      // row of image a the chunk starts at
+        for (int base = warp * 4; base < n_keep; base += 4 * (kScanThreads / 32)) {
+            const int ordinal = base + sub;
+            const bool have = ordinal < n_keep;
+            int r = 0;
+            if (have) {
+                const int c0 = __popc(keep_words[0]);
+                r = ordinal < c0 ? (int)__fns(keep_words[0], 0, ordinal + 1)
+                                 : 32 + (int)__fns(keep_words[1], 0, ordinal - c0 + 1);
+            }
             const float* row = buf + r * L;
-            const float obj = row[4];
+            const float obj = have ? row[4] : 0.0f;
             const float m = obj > conf ? 1.0f : 0.0f;
             float best = -INFINITY;
             int best_idx = 0x7fffffff;
-            for (int j = lane; j < C; j += 32) {
-                const float v = __fmul_rn(row[5 + j], m);
-                const bool take = (best_idx == 0x7fffffff) || (v > best) || (v != v && best == best);
-                if (take) {
-                    best = v;
-                    best_idx = j;
+            if (have)
+                for (int j = l8; j < C; j += 8) {
+                    const float v = __fmul_rn(row[5 + j], m);
+                    const bool take = (best_idx == 0x7fffffff) || (v > best) || (v != v && best == best);
+                    if (take) {
+                        best = v;
+                        best_idx = j;
+                    }
                 }
-            }
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
+            for (int off = 4; off > 0; off >>= 1) {                  // stays inside the 8-lane group
                 const float ov = __shfl_xor_sync(0xffffffffu, best, off);
                 const int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
                 const bool a_nan = best != best, b_nan = ov != ov;
@@ -251,15 +262,19 @@ nms_scan_kernel(const float* __restrict__ pred, long long total_rows, int N, int
                     best_idx = oi;
                 }
             }
-            if (lane == 0) {
-                const long long grow = first + r;
-                const long long img = grow / N;
-                const int row_in_img = (int)(grow - img * N);
-                int slot;
+            if (have && l8 == 0) {
+                long long img;
+                int row_in_img, slot;
                 if (grouped) {
-                    if (r < split) slot = slot_base[0] + ordinal;
-                    else slot = slot_base[1] + ordinal - __popcll(kmask & ((1ull << split) - 1ull));
+                    const bool in_a = r < split;
+                    img = in_a ? img_a : img_a + 1;
+                    row_in_img = in_a ? row_a0 + r : r - split;
+                    slot = in_a ? slot_base[0] + ordinal
+                                : slot_base[1] + ordinal - __popcll(kmask & ((1ull << split) - 1ull));
                 } else {
+                    const long long grow = first + r;
+                    img = grow / N;
+                    row_in_img = (int)(grow - img * N);
                     slot = atomicAdd(&cand_count[img], 1);
                 }
                 unsigned long long key = kDeadKey;
