@@ -277,15 +277,18 @@ __global__ void maxpool_kernel(Act in, Act out, int B, int size, int step, int c
 // bilinear x2, align_corners=False: even rows .25/.75 of (i-1, i), odd rows .75/.25 of (i, i+1),
 // indices clamped at the border; evaluated like ATen: h0*(w0*a + w1*b) + h1*(w0*c + w1*d)
 // ---------------------------------------------------------------------------------------------
+// Index: 32-bit where the tensor allows (64-bit divides cost ~100 instructions each; the kernel was issue-bound)
+template <typename Index>
 __global__ void upsample2x_kernel(Act in, Act out, int B) {
     const int groups = out.C / 8;
-    const long long total = (long long)B * out.H * out.W * groups;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int g = (int)(i % groups);
-        const int ox = (int)((i / groups) % out.W);
-        const int oy = (int)((i / ((long long)groups * out.W)) % out.H);
-        const int b = (int)(i / ((long long)groups * out.W * out.H));
+    const Index total = (Index)B * out.H * out.W * groups;
+    for (Index i = blockIdx.x * (Index)blockDim.x + threadIdx.x; i < total; i += (Index)gridDim.x * blockDim.x) {
+        const Index pix = i / (Index)groups;
+        const int g = (int)(i - pix * (Index)groups);
+        const Index line = pix / (Index)out.W;
+        const int ox = (int)(pix - line * (Index)out.W);
+        const int b = (int)(line / (Index)out.H);
+        const int oy = (int)(line - (Index)b * (Index)out.H);
         const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.0f), sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.0f);
         const int y0 = (int)sy, x0 = (int)sx;
         const int y1 = min(y0 + 1, in.H - 1), x1 = min(x0 + 1, in.W - 1);
@@ -429,7 +432,8 @@ int launch_maxpool(Act in, Act out, int B, int size, int stride, cudaStream_t st
 int launch_upsample2x(Act in, Act out, int B, cudaStream_t stream) {
     if (in.C % 8 != 0 || in.fp32 || out.fp32) return fail(RTOD_ERR_UNSUPPORTED, "upsample needs bf16, C%%8==0");
     const long long total = (long long)B * out.H * out.W * (out.C / 8);
-    upsample2x_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, out, B);
+    if (total < (1ll << 31)) upsample2x_kernel<unsigned><<<grid_for(total, 256), 256, 0, stream>>>(in, out, B);
+    else upsample2x_kernel<long long><<<grid_for(total, 256), 256, 0, stream>>>(in, out, B);
     RTOD_LAUNCH_OK("upsample2x_kernel");
     return RTOD_OK;
 }
