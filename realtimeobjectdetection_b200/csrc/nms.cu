@@ -164,7 +164,23 @@ nms_scan_kernel(const float* __restrict__ pred, long long total_rows, int N, int
     for (int pre = 0; pre < kScanStages - 1; ++pre)
         if (c + (long long)pre * gridDim.x < n_chunks) prefetch(c + (long long)pre * gridDim.x, pre);
     const bool grouped = N >= rows_per_chunk;                 // a chunk touches at most two images
+    // (image, row) of the chunk's first row advance by carried additions: no 64-bit divide per chunk and thread
+    const long long adv = (long long)gridDim.x * rows_per_chunk;
+    const long long step_img = adv / N;
+    const int step_row = (int)(adv - step_img * N);
+    long long img_a = (c * rows_per_chunk) / N;
+    int row_a0 = (int)(c * rows_per_chunk - img_a * N);
+    bool first_iter = true;
     for (int it = 0; c < n_chunks; ++it, c += gridDim.x) {
+        if (!first_iter) {
+            img_a += step_img;
+            row_a0 += step_row;
+            if (row_a0 >= N) {
+                row_a0 -= N;
+                ++img_a;
+            }
+        }
+        first_iter = false;
         const int s = it % kScanStages;
         if (chunk_is_bulk(c)) {
             if (tid == 0) {                               // one waiter; barrier (A) publishes the data
@@ -186,8 +202,7 @@ nms_scan_kernel(const float* __restrict__ pred, long long total_rows, int N, int
         const float* buf = stage_buf[s];
         const long long first = c * rows_per_chunk;
         const int rows = (int)((total_rows - first) < rows_per_chunk ? (total_rows - first) : rows_per_chunk);
-        const long long img_a = first / N;
-        const int split = (int)((img_a + 1) * (long long)N - first);   // rows of image a in this chunk
+        const int split = N - row_a0;                     // rows of image a in this chunk
 
         // (a) warp 0: objectness threshold (strict '>' in fp32, then "masked objectness != 0") for all
         //     rows (two per lane), and one atomicAdd per image touched to reserve contiguous slots
@@ -223,7 +238,6 @@ nms_scan_kernel(const float* __restrict__ pred, long long total_rows, int N, int
         //     64-bit sort key, append to the image's candidate list
         const int n_keep = __popcll(kmask);
         const int sub = lane >> 3, l8 = lane & 7;
-        const int row_a0 = (int)(first - img_a * (long long)N);      // row of image a the chunk starts at
         for (int base = warp * 4; base < n_keep; base += 4 * (kScanThreads / 32)) {
             const int ordinal = base + sub;
             const bool have = ordinal < n_keep;
