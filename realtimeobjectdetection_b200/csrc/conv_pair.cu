@@ -262,7 +262,7 @@ int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     store_fastdiv(p.fd_wo, (uint32_t)a.out.W);
     store_fastdiv(p.fd_howo, (uint32_t)(a.out.W * a.out.H));
     launch->patch = 2;
-    launch->choice = ConvTcChoice{1, 0, p.stage_bufs, 1, 256, 1};
+    launch->choice = ConvTcChoice{1, 0, p.stage_bufs, 1, 256, 1, 8, 1};
     p.split_k = 1; p.split_shift = 0; p.split_scratch = nullptr; p.split_count = nullptr;
     launch->smem_bytes = stages * stage_bytes + fixed;
     RTOD_CUDA_OK(cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

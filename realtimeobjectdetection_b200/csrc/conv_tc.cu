@@ -438,6 +438,10 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
         const uint32_t cap = ctas == 1 ? kSmemLimit : (227u * 1024u) / ctas - 2048u;
         int ew = (ctas == 1 && BN >= 128) ? 8 : 4;
         if (env_ew && (atoi(env_ew) == 4 || (atoi(env_ew) == 8 && BN >= 128))) ew = atoi(env_ew);
+        if (force && force->ew) {
+            if (force->ew == 8 && BN < 128) continue;
+            ew = force->ew;
+        }
         for (int opt = 0; opt < 4 && stages == 0; ++opt) {
             const bool resident = may_reside && (opt & 1) == 0;
             const int sbufs = (opt & 2) ? 1 : 2;
@@ -475,9 +479,13 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
         p.split_scratch = a.split_scratch;
         p.split_count = a.split_count;
     }
-    launch->choice = ConvTcChoice{ctas_per_sm, p.b_resident, p.stage_bufs, 0, BN, p.split_k};
+    launch->choice = ConvTcChoice{ctas_per_sm, p.b_resident, p.stage_bufs, 0, BN, p.split_k, epi_warps, p.a_producers};
     // im2col issue costs a thread ~350 cycles: two alternating A producers when a k-block's MMAs take less
     p.a_producers = (a.ks > 1 && (BK / 16) * (BN / 2) < 350 && getenv("RTOD_TC_ONE_A") == nullptr) ? 2 : 1;
+    if (force && force->ap) {
+        if (force->ap == 2 && (a.ks == 1 || stages < 2)) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: two activation producers need a gather");
+        p.a_producers = force->ap;
+    }
     {   // channels per epilogue chunk: one 128-byte staging row, narrower if the tile has fewer columns per group
         const int per_group = BN / (epi_warps / 4);
         p.ecols = a.out.fp32 ? 32 : (per_group < 64 ? per_group : 64);
@@ -613,8 +621,11 @@ int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cud
                     if (pair && (bn != 256 || ctas != 1 || resident != 0 || sbufs != 2)) continue;   // one pair configuration
                     if (!pair && bn > a.Cout_pad) continue;
                     if (sbufs == 1 && a.res) continue;       // the shortcut operand is prefetched into the 2nd slice
-                  {
-                    const ConvTcChoice c{ctas, resident, sbufs, pair, bn, 0};
+                  for (int ew = 4; ew <= 8; ew += 4)
+                   for (int ap = 1; ap <= 2; ++ap) {
+                    if (pair && (ew != 8 || ap != 1)) continue;
+                    if (!pair && ((ew == 8 && (bn < 128 || ctas == 3)) || (ap == 2 && a.ks == 1))) continue;
+                    const ConvTcChoice c{ctas, resident, sbufs, pair, bn, 0, pair ? 0 : ew, pair ? 0 : ap};
                     cand = ConvTcLaunch{};
                     if (conv_tc_prepare(a, err_flag, &cand, &c) != RTOD_OK) continue;      // does not fit / apply
                     float ms;
@@ -630,9 +641,9 @@ int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cud
     if (rc) return rc;
     *launch = best;
     if (getenv("RTOD_TC_TUNE_DBG"))
-        fprintf(stderr, "conv_tc_autotune: M %d Cin %d Cout %d ks %d s %d -> %s BN %d ctas %d resident %d sbufs %d split %d stages %d (%.1f us)\n",
+        fprintf(stderr, "conv_tc_autotune: M %d Cin %d Cout %d ks %d s %d -> %s BN %d ctas %d resident %d sbufs %d split %d epi %d aprod %d stages %d (%.1f us)\n",
                 a.B * a.out.H * a.out.W, a.Cin, a.Cout, a.ks, a.stride, best.patch == 2 ? "pair" : "tc", best.choice.bn, best.choice.ctas,
-                best.choice.resident, best.choice.sbufs, best.choice.split, best.p.stages, best_ms * 1e3f);
+                best.choice.resident, best.choice.sbufs, best.choice.split, best.p.epi_warps, best.p.a_producers, best.p.stages, best_ms * 1e3f);
     return RTOD_OK;
 }
 

@@ -61,7 +61,8 @@ struct alignas(64) ConvPatchParams {
 struct ConvTcChoice {           // one launch configuration of conv_tc_kernel (or the CTA-pair kernel)
     int ctas, resident, sbufs, pair;
     int bn;                     // N tile (0 = heuristic)
-    int split;                  // K slices per tile (0/1 = no split-K)
+    int split;                  // K slices per tile (0 = by shape)
+    int ew, ap;                 // epilogue warps (4 / 8), activation producer threads (1 / 2); 0 = heuristic
 };
 
 struct ConvTcLaunch {           // host side: kernel parameters + launch geometry
