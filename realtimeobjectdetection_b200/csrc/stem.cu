@@ -33,7 +33,7 @@ struct StemParams {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(448, 2) stem_tma_kernel(const __grid_constant__ StemParams p) {
+__global__ void __launch_bounds__(224, 4) stem_tma_kernel(const __grid_constant__ StemParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 127u) & ~127u) - raw_addr);
@@ -218,11 +218,11 @@ int launch_stem_tma(const float* x, int B, int H, int W, const float* w, const f
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (stem image) failed: %d", (int)r);
     int warps = p.tiles_per_strip;
-    if (warps > 14) warps = (warps + 1) / 2;                    // two tiles per warp and strip
-    if (warps > 14) warps = 14;
+    if (warps > 7) warps = (warps + 1) / 2;                     // two tiles per warp and strip
+    if (warps > 7) warps = 7;
     if (warps < 2) warps = 2;
     const size_t smem = (size_t)kStemStages * (((size_t)9 * p.box_w * 4 + 127) & ~(size_t)127) + kStemStages * 8 + 16 + 256;
-    const int per_sm = 2;                                        // <= 72 registers/thread: two CTAs of <= 14 warps per SM
+    const int per_sm = 4;                                        // <= 72 registers/thread: four CTAs of <= 7 warps per SM
     int grid = kNumSMs * per_sm;
     if (grid > p.total_strips) grid = p.total_strips;
     if (Cout == 32) stem_tma_kernel<4><<<grid, warps * 32, smem, stream>>>(p);
