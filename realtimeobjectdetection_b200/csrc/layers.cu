@@ -231,15 +231,17 @@ __global__ void nhwc_to_nchw_kernel(Act in, int B, float* __restrict__ out) {
 // max-pool: MaxPool2d(size, stride) (floor mode, no padding) or, for stride 1, the reference's
 // MaxPoolStride1: replicate-pad right/bottom by size-1, then pool with stride size-1
 // ---------------------------------------------------------------------------------------------
+template <typename Index>                                   // 32-bit index arithmetic where the tensor allows
 __global__ void maxpool_kernel(Act in, Act out, int B, int size, int step, int clamp_edge) {
     const int groups = out.C / 8;
-    const long long total = (long long)B * out.H * out.W * groups;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int g = (int)(i % groups);
-        const int ox = (int)((i / groups) % out.W);
-        const int oy = (int)((i / ((long long)groups * out.W)) % out.H);
-        const int b = (int)(i / ((long long)groups * out.W * out.H));
+    const Index total = (Index)B * out.H * out.W * groups;
+    for (Index i = blockIdx.x * (Index)blockDim.x + threadIdx.x; i < total; i += (Index)gridDim.x * blockDim.x) {
+        const Index pix = i / (Index)groups;
+        const int g = (int)(i - pix * (Index)groups);
+        const Index line = pix / (Index)out.W;
+        const int ox = (int)(pix - line * (Index)out.W);
+        const int b = (int)(line / (Index)out.H);
+        const int oy = (int)(line - (Index)b * (Index)out.H);
         const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(in.ptr) + g * 8;
         __nv_bfloat162 best[4];
         bool first = true;
@@ -423,8 +425,10 @@ int launch_maxpool(Act in, Act out, int B, int size, int stride, cudaStream_t st
     if (in.C % 8 != 0 || in.fp32 || out.fp32) return fail(RTOD_ERR_UNSUPPORTED, "maxpool needs bf16, C%%8==0");
     const long long total = (long long)B * out.H * out.W * (out.C / 8);
     const int step = stride != 1 ? stride : size - 1;           // src/darknet.py:35,45
-    maxpool_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, out, B, size, step < 1 ? 1 : step,
-                                                             stride == 1);
+    if (total < (1ll << 31))
+        maxpool_kernel<unsigned><<<grid_for(total, 256), 256, 0, stream>>>(in, out, B, size, step < 1 ? 1 : step, stride == 1);
+    else
+        maxpool_kernel<long long><<<grid_for(total, 256), 256, 0, stream>>>(in, out, B, size, step < 1 ? 1 : step, stride == 1);
     RTOD_LAUNCH_OK("maxpool_kernel");
     return RTOD_OK;
 }
