@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RTOD_ABI_VERSION 1
+#define RTOD_ABI_VERSION 2
 
 enum {
     RTOD_OK = 0,
@@ -74,6 +74,8 @@ typedef struct RtodPlan RtodPlan;
 #define RTOD_PLAN_KEEP_ALL 1u     /* no buffer reuse: every layer output stays readable    */
 #define RTOD_PLAN_CONV_SIMT 2u    /* validation only: CUDA-core convs instead of tcgen05   */
 #define RTOD_PLAN_NO_AUTOTUNE 4u  /* bind: heuristic launch configurations, no timing runs */
+#define RTOD_PLAN_BF16 8u         /* bf16 activations/weights (default: fp16, same tensor rate, 8x finer rounding) */
+#define RTOD_PLAN_NO_WSPLIT 16u   /* fp16 only: no two-term weights in the HBM-bound early layers           */
 
 int rtod_abi_version(void);
 const char* rtod_last_error(void);
@@ -130,7 +132,7 @@ enum {
     RTOD_CONV_STEM = 1,      /* stem.cu: 3-channel fp32 NCHW image -> NHWC bf16                  */
     RTOD_CONV_TC = 2,        /* conv_tc.cu: tcgen05 implicit GEMM, one CTA per tile              */
     RTOD_CONV_TC_PAIR = 3,   /* conv_pair.cu: tcgen05 cta_group::2, one CTA pair per 256x256 tile */
-    RTOD_CONV_TC_PATCH = 4,  /* conv_patch.cu: halo-patch 3x3 variant (opt-in)                   */
+    RTOD_CONV_TC_PATCH = 4,  /* retired (halo-patch 3x3 variant); never returned                 */
     RTOD_CONV_SIMT = 5       /* conv_simt.cu: CUDA-core validation path (RTOD_PLAN_CONV_SIMT)     */
 };
 int rtod_plan_conv_backend(const RtodPlan* plan, int layer);
@@ -140,6 +142,17 @@ int rtod_plan_conv_backend(const RtodPlan* plan, int layer);
 int rtod_plan_read_layer(RtodPlan* plan, int layer, float* out_nchw, void* stream);
 /* Polls the device-side failure flag of the last forward (synchronises the stream). */
 int rtod_plan_check(RtodPlan* plan, void* stream);
+/* Failure reporting without a synchronisation: `host_flag` is a pinned (device-mapped, UVA) host int owned by
+ * the caller; a kernel that times out stores its failure code there, the caller polls it between calls.
+ * Null detaches.  Enqueued on `stream`. */
+int rtod_plan_set_error_sink(RtodPlan* plan, int* host_flag, void* stream);
+/* After a reported failure: clears the device flag and the split-K arrival counters (a timed-out layer leaves
+ * them mid-count), so that the next forward starts clean.  Enqueued on `stream`. */
+int rtod_plan_reset_errors(RtodPlan* plan, void* stream);
+/* 1 = the plan stores activations/weights as fp16, 0 = bf16 */
+int rtod_plan_is_f16(const RtodPlan* plan);
+/* 1 = convolution `layer` keeps two-term (hi + lo) weights */
+int rtod_plan_conv_w_split(const RtodPlan* plan, int layer);
 
 /* ---- util.predict_transform (src/util.py:175-239) -------------------------------------
  * head: [B, A*(5+C), G, G] fp32 NCHW -> out: [B, G*G*A, 5+C] fp32; anchors_host: A (w,h) pixel
@@ -168,6 +181,34 @@ int rtod_confidence_mask(const float* pred, long long rows, int attrs, float con
  * every operation individually rounded like the reference's tensor ops). */
 int rtod_bbox_iou(const float* box1, int n1, int stride1, const float* box2, int n2, int stride2,
                   float* out, void* stream);
+
+/* ---- util.prep_image / letterbox_image (src/util.py:349-397) -------------------------------
+ * src: [B, src_h, src_w, 3] uint8 HWC frames (BGR, as cv2.imread delivers them), all of one size.
+ * out: [B, 3, inp_dim, inp_dim], fp32 (value / 255, what prep_image returns) or uint8 planes (out_u8 != 0).
+ * The frame is resized with cv2.INTER_CUBIC semantics to (new_w, new_h) = rtod_letterbox_geometry and pasted
+ * on a canvas filled with 128; channels are reversed (BGR -> RGB, prep_image's default mode) unless keep_order.
+ * resize_mode 0: fp32 cubic weights (the stock opencv-python wheel routes 8-bit cubic resizes to IPP; equal to it
+ * to within one grey level on < 0.03 % of the values); 1: OpenCV's own fixed-point path, bit-identical to
+ * cv2.resize built/run without IPP. */
+int rtod_letterbox_geometry(int src_w, int src_h, int inp_dim, int* new_w, int* new_h, int* left, int* top);
+int rtod_prep_image(const unsigned char* src, int B, int src_h, int src_w, int inp_dim, int keep_order,
+                    int resize_mode, int out_u8, void* out, void* stream);
+
+/* ---- Darknetv3Detector.convert_box_dims_to_original_image + clamp_box_dims (detect.py:120-136) --------
+ * rows: [D, 8] write_results rows whose column 0 indexes im_dims; im_dims: [n_img, 4] fp32 (w, h, w, h)
+ * (detect.py:247-248).  out_rows: [D, 8] with columns 1..4 mapped to source-image pixels and clamped to
+ * [0, w] / [0, h]; out_dims (may be null): [D, 4] the im_dims row of every detection (the reference returns it).
+ * The scale is min(ref_dim / w, ref_dim / h) -- the reference hard-codes ref_dim = 416 (detect.py:130) --
+ * the centring offset uses inp_dim (:131-134). */
+int rtod_rescale_boxes(const float* rows, int D, const float* im_dims, int n_img, int inp_dim, int ref_dim,
+                       float* out_rows, float* out_dims, void* stream);
+
+/* ---- DarknetValidator.create_iou_matrix_for_predictions_and_targets (test.py:139-151) ------------------
+ * out[p * T + t] = bbox_iou(pred_boxes[p], target_boxes[t]) (rows of `stride` floats starting with
+ * x1,y1,x2,y2: pass pred + 1 for write_results rows), zeroed unless (double)iou > threshold when
+ * use_threshold != 0 (the reference compares Python floats). */
+int rtod_bbox_iou_matrix(const float* pred_boxes, int P, int pred_stride, const float* target_boxes, int T,
+                         int target_stride, int use_threshold, double threshold, float* out, void* stream);
 
 /* ---- measurement aid (bench.py "clocks"; no reference counterpart) ------------------------
  * One thread samples the SM clock it runs on: `samples` windows of `interval_us` microseconds,

@@ -21,3 +21,4 @@ NMS-idempotence known-answer test (tests/test_oracle_golden.py).
 from .detect_port import (bbox_iou, confidence_mask, predict_transform,  # noqa: F401
                           write_results)
 from .darknet_port import DarknetPort, parse_cfg  # noqa: F401
+from . import post_port, prep_port  # noqa: F401

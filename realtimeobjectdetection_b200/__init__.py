@@ -11,9 +11,11 @@ calling it does, and there is no CPU fallback.
 """
 from .cfg import builtin_cfg, parse_cfg  # noqa: F401
 from .darknet import Darknet, DetectionLayer, EmptyLayer, MaxPoolStride1  # noqa: F401
-from .util import (bbox_iou, confidence_mask, predict_transform, write_results,  # noqa: F401
+from .util import (bbox_iou, bbox_iou_matrix, confidence_mask, letterbox_image, metrics_rows,  # noqa: F401
+                   predict_transform, prep_frames, prep_image, rescale_boxes, write_results,
                    write_results_async)
 
 __all__ = ["Darknet", "DetectionLayer", "EmptyLayer", "MaxPoolStride1", "bbox_iou",
-           "confidence_mask", "predict_transform", "write_results", "write_results_async", "builtin_cfg",
-           "parse_cfg"]
+           "bbox_iou_matrix", "confidence_mask", "letterbox_image", "metrics_rows", "predict_transform",
+           "prep_frames", "prep_image", "rescale_boxes", "write_results", "write_results_async",
+           "builtin_cfg", "parse_cfg"]

@@ -14,13 +14,15 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librtod.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 RTOD_MAX_ANCHORS = 8
 LAYER_CONV, LAYER_SHORTCUT, LAYER_ROUTE, LAYER_UPSAMPLE, LAYER_MAXPOOL, LAYER_YOLO = range(6)
 PLAN_KEEP_ALL = 1
 PLAN_CONV_SIMT = 2
 PLAN_NO_AUTOTUNE = 4
+PLAN_BF16 = 8            # bf16 storage (default: fp16)
+PLAN_NO_WSPLIT = 16      # fp16: no two-term weights in the HBM-bound early layers
 
 
 class RtodError(RuntimeError):
@@ -65,12 +67,21 @@ _PROTOTYPES = {
     "rtod_plan_conv_backend": (_i, [_vp, _i]),
     "rtod_plan_read_layer": (_i, [_vp, _i, _vp, _vp]),
     "rtod_plan_check": (_i, [_vp, _vp]),
+    "rtod_plan_set_error_sink": (_i, [_vp, _vp, _vp]),
+    "rtod_plan_reset_errors": (_i, [_vp, _vp]),
+    "rtod_plan_is_f16": (_i, [_vp]),
+    "rtod_plan_conv_w_split": (_i, [_vp, _i]),
     "rtod_yolo_decode": (_i, [_vp, _i, _i, _i, _i, _i, ctypes.POINTER(_f), _i, _vp, _vp]),
     "rtod_write_results_workspace_bytes": (_sz, [_i, _i, _i]),
     "rtod_write_results": (_i, [_vp, _i, _i, _i, _f, _f, _vp, _i, _vp, _vp, _sz, _vp]),
     "rtod_confidence_mask": (_i, [_vp, ctypes.c_longlong, _i, _f, _vp, _vp]),
     "rtod_bbox_iou": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp]),
     "rtod_sm_clock_probe": (_i, [_vp, _i, _i, _vp]),
+    "rtod_letterbox_geometry": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i),
+                                     ctypes.POINTER(_i)]),
+    "rtod_prep_image": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rtod_rescale_boxes": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "rtod_bbox_iou_matrix": (_i, [_vp, _i, _i, _vp, _i, _i, _i, ctypes.c_double, _vp, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(sorted(_PROTOTYPES))
 

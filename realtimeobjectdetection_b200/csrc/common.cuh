@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -58,6 +59,36 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// 16-bit activation / weight storage: fp16 (default: 11 significant bits, what the prediction-tensor tolerance
+// needs on a non-degenerate network) or bf16 (the north-star wording; 8 bits).  Same tcgen05 kind::f16 rate.
+// fp16 packing saturates to +-65504 instead of producing inf.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float f16_lo(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xFFFFu))); }
+__device__ __forceinline__ float f16_hi(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
+template <bool kF16> __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    if constexpr (kF16) return pack_f16x2(lo, hi);
+    else return pack_bf16x2(lo, hi);
+}
+template <bool kF16> __device__ __forceinline__ float h2_lo(uint32_t v) {
+    if constexpr (kF16) return f16_lo(v);
+    else return bf16_lo(v);
+}
+template <bool kF16> __device__ __forceinline__ float h2_hi(uint32_t v) {
+    if constexpr (kF16) return f16_hi(v);
+    else return bf16_hi(v);
+}
+template <bool kF16> __device__ __forceinline__ float h1_to_float(unsigned short v) {
+    if constexpr (kF16) return __half2float(__ushort_as_half(v));
+    else return __uint_as_float((uint32_t)v << 16);
+}
+template <bool kF16> __device__ __forceinline__ unsigned short float_to_h1(float v) {
+    return (unsigned short)(pack_h2<kF16>(v, 0.0f) & 0xFFFFu);
+}
 
 // logistic function (reference: torch.sigmoid, fp32): full-precision exp, reciprocal by MUFU.RCP (<= 1 ulp;
 // 1 + exp(-v) is never denormal, so the flush-to-zero variant is exact in range).  The correctly rounded

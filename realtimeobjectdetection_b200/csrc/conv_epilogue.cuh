@@ -1,5 +1,5 @@
 // conv_epilogue.cuh -- epilogue shared by the tcgen05 convolution kernels (conv_tc.cu, conv_pair.cu):
-// accumulator (TMEM) -> + folded bias -> leaky 0.1 -> + shortcut operand -> bf16 (fp32 for head logits)
+// accumulator (TMEM) -> + folded bias -> leaky 0.1 -> + shortcut operand -> fp16 / bf16 (fp32 for head logits)
 // -> swizzled shared memory -> TMA store (src/darknet.py:292-295 BN/LeakyReLU, :263-268 shortcut).
 //
 // Every epilogue warp is its own pipeline -- no CTA-level barrier: warp w may only read TMEM lanes
@@ -21,7 +21,7 @@ constexpr uint32_t kEpiSlice = 4096;            // one warp's staging slice: 32 
 // release(buf): arrive on the accumulator-empty barrier the MMA issuer waits on (called by one lane)
 // The TMA / bulk-group / mbarrier-arrive instructions of a warp are always issued by its elect.sync lane
 // (deterministic for a full mask), so the per-thread bulk async-groups stay with one thread.
-template <int kEpiWarps, class Origin, class Release>
+template <int kEpiWarps, bool kF16, class Origin, class Release>
 static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint32_t tmem_base, uint64_t* acc_full,
                                                      uint8_t* epi_stage, uint64_t* res_bar, int ew, int lane,
                                                      int tile_first, int tile_step, Origin origin, Release release) {
@@ -111,16 +111,16 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
                         const uint32_t off = staged_offset(lane, h * 4 + q, erow);
                         if (p.has_res) {
                             const uint4 r = *reinterpret_cast<const uint4*>(slice + off);
-                            f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
-                            f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
-                            f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
-                            f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+                            f[0] += h2_lo<kF16>(r.x); f[1] += h2_hi<kF16>(r.x);
+                            f[2] += h2_lo<kF16>(r.y); f[3] += h2_hi<kF16>(r.y);
+                            f[4] += h2_lo<kF16>(r.z); f[5] += h2_hi<kF16>(r.z);
+                            f[6] += h2_lo<kF16>(r.w); f[7] += h2_hi<kF16>(r.w);
                         }
                         uint4 o;
-                        o.x = pack_bf16x2(f[0], f[1]);
-                        o.y = pack_bf16x2(f[2], f[3]);
-                        o.z = pack_bf16x2(f[4], f[5]);
-                        o.w = pack_bf16x2(f[6], f[7]);
+                        o.x = pack_h2<kF16>(f[0], f[1]);
+                        o.y = pack_h2<kF16>(f[2], f[3]);
+                        o.z = pack_h2<kF16>(f[4], f[5]);
+                        o.w = pack_h2<kF16>(f[6], f[7]);
                         *reinterpret_cast<uint4*>(slice + off) = o;
                     }
                 }
@@ -157,7 +157,7 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
 // accumulator to scratch[tile][slice][128][BN]; a per-tile counter elects the LAST CTA to arrive, which
 // sums the `split` partials in slice order (deterministic, independent of arrival order) and runs the
 // normal bias / leaky / shortcut / store path.  work(i, tile, slice) enumerates this CTA's work items.
-template <int kEpiWarps, class Work, class Origin, class Release>
+template <int kEpiWarps, bool kF16, class Work, class Origin, class Release>
 static __device__ __forceinline__ void conv_epilogue_split(const ConvTcParams& p, uint32_t tmem_base,
                                                            uint64_t* acc_full, uint8_t* epi_stage, uint64_t* res_bar,
                                                            int* s_last, int ew, int lane, Work work, Origin origin,
@@ -256,16 +256,16 @@ static __device__ __forceinline__ void conv_epilogue_split(const ConvTcParams& p
                         const uint32_t off = staged_offset(lane, h * 4 + q, erow);
                         if (p.has_res) {
                             const uint4 r = *reinterpret_cast<const uint4*>(slice + off);
-                            f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
-                            f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
-                            f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
-                            f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+                            f[0] += h2_lo<kF16>(r.x); f[1] += h2_hi<kF16>(r.x);
+                            f[2] += h2_lo<kF16>(r.y); f[3] += h2_hi<kF16>(r.y);
+                            f[4] += h2_lo<kF16>(r.z); f[5] += h2_hi<kF16>(r.z);
+                            f[6] += h2_lo<kF16>(r.w); f[7] += h2_hi<kF16>(r.w);
                         }
                         uint4 o;
-                        o.x = pack_bf16x2(f[0], f[1]);
-                        o.y = pack_bf16x2(f[2], f[3]);
-                        o.z = pack_bf16x2(f[4], f[5]);
-                        o.w = pack_bf16x2(f[6], f[7]);
+                        o.x = pack_h2<kF16>(f[0], f[1]);
+                        o.y = pack_h2<kF16>(f[2], f[3]);
+                        o.z = pack_h2<kF16>(f[4], f[5]);
+                        o.w = pack_h2<kF16>(f[6], f[7]);
                         *reinterpret_cast<uint4*>(slice + off) = o;
                     }
                 }

@@ -27,6 +27,7 @@ namespace {
 constexpr int kEpilogueWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpilogueWarps;
 
+template <bool kF16>
 __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_constant__ ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
         }
     } else {
         // ================= epilogue (conv_epilogue.cuh): each CTA stores its own 128 rows =================
-        conv_epilogue<kEpilogueWarps>(
+        conv_epilogue<kEpilogueWarps, kF16>(
             p, tmem_base, acc_full, epi_stage, res_full, warp - 2, lane, tile_first, tile_step,
             [&](int tile, int& m0, int& n0) {
                 const int n_tile = (int)fast_div((uint32_t)tile, p.fd_mtiles);
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
 
 bool conv_pair_eligible(const ConvArgs& a) {
     if (getenv("RTOD_TC_NO_PAIR")) return false;
-    if (a.Cout_pad % 256 != 0 || a.out.fp32) return false;
+    if (a.Cout_pad % 256 != 0 || a.out.fp32 || a.w_split) return false;      // two-term weights: one-CTA kernel only
     const long long m_tiles = ((long long)a.B * a.out.H * a.out.W + kBM - 1) / kBM;
     return ((m_tiles + 1) / 2) * (a.Cout_pad / 256) >= 60;          // enough pair tiles to fill 74 SM pairs
 }
@@ -245,8 +246,8 @@ int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     p.Ho = a.out.H; p.Wo = a.out.W; p.stride = a.stride; p.pad = a.pad;
     p.tmem_cols = 512; p.has_res = a.res != nullptr; p.ecols = 64; p.b_resident = 0; p.stage_bufs = 2;
     p.dbg = (getenv("RTOD_PAIR_MODE") ? atoi(getenv("RTOD_PAIR_MODE")) : 0) | (getenv("RTOD_CLK_DBG") ? 8 : 0);
-    // M = 256 per pair (m_dim = 256 >> 4), N = 256
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    p.f16 = a.in.f16; p.w_split = 0; p.cout_pad = a.Cout_pad;
+    p.idesc = umma_idesc(p.f16, 256, BN);               // M = 256 per pair, N = 256
     const uint32_t stage_bytes = (uint32_t)(kBM + BN / 2) * BK * 2;
     p.epi_warps = kEpilogueWarps;
     if (const char* e = getenv("RTOD_TC_SBUFS")) p.stage_bufs = atoi(e) == 1 ? 1 : 2;
@@ -265,10 +266,11 @@ int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     launch->choice = ConvTcChoice{1, 0, p.stage_bufs, 1, 256, 1, 8, 1};
     p.split_k = 1; p.split_shift = 0; p.split_scratch = nullptr; p.split_count = nullptr;
     launch->smem_bytes = stages * stage_bytes + fixed;
-    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     // clusters that can be resident at once (pairs must share a TPC): the persistent tile loop
     // strides by the grid, so a cluster that only starts in a second wave would double the time
-    static int max_clusters = 0;
+    static int max_clusters = 0;                         // same for every B200 of a box: queried once
     if (!max_clusters) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(kNumSMs, 1, 1);
@@ -281,7 +283,7 @@ int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        RTOD_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, conv_pair_kernel, &cfg));
+        RTOD_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, conv_pair_kernel<true>, &cfg));
         if (const char* e = getenv("RTOD_PAIR_CLUSTERS")) max_clusters = atoi(e);
         if (getenv("RTOD_PAIR_DBG")) fprintf(stderr, "conv_pair: %d resident clusters\n", max_clusters);
         if (max_clusters < 1) return fail(RTOD_ERR_CUDA, "conv_pair: no resident cluster fits");
@@ -295,7 +297,7 @@ int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
         const cuuint64_t dims[2] = {(cuuint64_t)a.Cin, (cuuint64_t)M};
         const cuuint64_t strides[1] = {(cuuint64_t)a.in.pitch * 2};
         const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)kBM};
-        r = encode_tiled(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.in.ptr, dims, strides, box, estr1,
+        r = encode_tiled(&p.tmA, h16_tmap_type(a.in.f16), 2, a.in.ptr, dims, strides, box, estr1,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
@@ -305,7 +307,7 @@ int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
         const int lower[2] = {-a.pad, -a.pad};
         const int upper[2] = {a.pad - (a.ks - 1), a.pad - (a.ks - 1)};
         const cuuint32_t estr[4] = {1, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1};
-        r = encode_im2col(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.in.ptr, dims, strides, lower, upper,
+        r = encode_im2col(&p.tmA, h16_tmap_type(a.in.f16), 4, a.in.ptr, dims, strides, lower, upper,
                           (cuuint32_t)BK, (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK),
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r == CUDA_SUCCESS && (unsigned long long)a.in.pitch * 2ull * a.in.W * a.in.H * a.B < 131072ull)
@@ -316,7 +318,7 @@ int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
         const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.Cout_pad};
         const cuuint64_t strides[1] = {(cuuint64_t)a.K * 2};
         const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(BN / 2)};
-        r = encode_tiled(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.w), dims, strides,
+        r = encode_tiled(&p.tmB, h16_tmap_type(a.in.f16), 2, const_cast<void*>(a.w), dims, strides,
                          box, estr1, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (pair weights) failed: %d", (int)r);
@@ -325,13 +327,13 @@ int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
         const cuuint64_t dims[2] = {(cuuint64_t)a.Cout, (cuuint64_t)M};
         const cuuint64_t strides[1] = {(cuuint64_t)a.out.pitch * 2};
         const cuuint32_t box[2] = {64, 32};                       // one epilogue warp's rows
-        r = encode_tiled(&p.tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.out.ptr, dims, strides, box, estr1,
+        r = encode_tiled(&p.tmOut, h16_tmap_type(a.in.f16), 2, a.out.ptr, dims, strides, box, estr1,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (pair output) failed: %d", (int)r);
         if (p.has_res) {
             const cuuint64_t rstrides[1] = {(cuuint64_t)a.res_pitch * 2};
-            r = encode_tiled(&p.tmRes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.res), dims,
+            r = encode_tiled(&p.tmRes, h16_tmap_type(a.in.f16), 2, const_cast<void*>(a.res), dims,
                              rstrides, box, estr1, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (pair shortcut) failed: %d", (int)r);
@@ -355,7 +357,8 @@ int conv_pair_launch(const ConvTcLaunch& launch, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_pair_kernel, launch.p));
+    if (launch.p.f16) RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_pair_kernel<true>, launch.p));
+    else RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_pair_kernel<false>, launch.p));
     return RTOD_OK;
 }
 

@@ -1,5 +1,5 @@
-// conv_simt.cu -- CUDA-core implicit-GEMM convolution over the same NHWC bf16 tensors, K-major
-// bf16 weights and fused epilogue (bias, leaky 0.1, shortcut add) as the tcgen05 kernel in
+// conv_simt.cu -- CUDA-core implicit-GEMM convolution over the same NHWC fp16/bf16 tensors, K-major
+// weights and fused epilogue (bias, leaky 0.1, shortcut add) as the tcgen05 kernel in
 // conv_tc.cu.  It is NOT the product path: it exists (a) as the on-device cross-check the
 // parity tests run next to the tcgen05 kernel (plan flag RTOD_PLAN_CONV_SIMT) and (b) for
 // shapes the tensor-core kernel does not tile (Cin not a multiple of 16, kernels other than
@@ -12,6 +12,7 @@ namespace {
 
 constexpr int BM = 64, BN = 64, BK = 16;
 
+template <bool kF16>
 __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
@@ -20,7 +21,9 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
     const long long m0 = (long long)blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
-    const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(a.in.ptr);
+    const unsigned short* in = reinterpret_cast<const unsigned short*>(a.in.ptr);
+    const unsigned short* w16 = reinterpret_cast<const unsigned short*>(a.w);
+    const unsigned short* res16 = reinterpret_cast<const unsigned short*>(a.res);
 
     float acc[4][4];
 #pragma unroll
@@ -41,14 +44,19 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
                 const long long b = m / ((long long)Wo * Ho);
                 const int iy = oy * a.stride - a.pad + ky, ix = ox * a.stride - a.pad + kx;
                 if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-                    v = __bfloat162float(in[((b * H + iy) * W + ix) * a.in.pitch + c]);
+                    v = h1_to_float<kF16>(in[((b * H + iy) * W + ix) * a.in.pitch + c]);
             }
             As[kk][mm] = v;
         }
         for (int e = tid; e < BN * BK; e += 256) {
             const int kk = e % BK, nn = e / BK;
             const int k = k0 + kk, n = n0 + nn;
-            Bs[kk][nn] = (k < a.K && n < a.Cout) ? __bfloat162float(a.w[(long long)n * a.K + k]) : 0.0f;
+            float wv = 0.0f;
+            if (k < a.K && n < a.Cout) {
+                wv = h1_to_float<kF16>(w16[(long long)n * a.K + k]);
+                if (a.w_split) wv += h1_to_float<kF16>(w16[(long long)(a.Cout_pad + n) * a.K + k]);      // hi + lo
+            }
+            Bs[kk][nn] = wv;
         }
         __syncthreads();
 #pragma unroll
@@ -76,9 +84,9 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
             if (n >= a.Cout) continue;
             float v = acc[i][j] + a.bias[n];
             if (a.leaky) v = leaky01(v);
-            if (a.res) v += __bfloat162float(a.res[m * a.res_pitch + n]);
+            if (a.res) v += h1_to_float<kF16>(res16[m * a.res_pitch + n]);
             if (a.out.fp32) reinterpret_cast<float*>(a.out.ptr)[m * a.out.pitch + n] = v;
-            else reinterpret_cast<__nv_bfloat16*>(a.out.ptr)[m * a.out.pitch + n] = __float2bfloat16_rn(v);
+            else reinterpret_cast<unsigned short*>(a.out.ptr)[m * a.out.pitch + n] = float_to_h1<kF16>(v);
         }
     }
 }
@@ -88,7 +96,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
 int launch_conv_simt(const ConvArgs& a, cudaStream_t stream) {
     const long long M = (long long)a.B * a.out.H * a.out.W;
     dim3 grid(ceil_div(M, BM), ceil_div(a.Cout, BN));
-    conv_simt_kernel<<<grid, 256, 0, stream>>>(a);
+    if (a.in.f16) conv_simt_kernel<true><<<grid, 256, 0, stream>>>(a);
+    else conv_simt_kernel<false><<<grid, 256, 0, stream>>>(a);
     RTOD_LAUNCH_OK("conv_simt_kernel");
     return RTOD_OK;
 }

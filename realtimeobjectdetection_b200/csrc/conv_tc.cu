@@ -49,7 +49,7 @@ constexpr uint32_t kResidentLimit = 100 * 1024; // largest weight matrix kept re
 // weight tile in L2).  The accumulator is double-buffered in TMEM, so the epilogue of tile i runs
 // while the tensor core already works on tile i+1, and the TMA producer runs ahead across tile
 // boundaries as far as the shared-memory ring allows.
-template <int kEpiWarps>
+template <int kEpiWarps, bool kF16>
 __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
     }
 #endif
     const uint32_t row_bytes = (uint32_t)p.BK * 2u;
-    const uint32_t a_bytes = kBM * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
+    // weight tile of one k-block: BN rows, twice that (hi rows, then lo rows) for split weights
+    const uint32_t a_bytes = kBM * row_bytes, b_half = (uint32_t)p.BN * row_bytes, b_bytes = b_half << p.w_split;
     const uint32_t stage_bytes = a_bytes + (p.b_resident ? 0u : b_bytes);
     // ring stages hold {A, B} tiles, or A tiles only when the whole weight matrix is resident
     uint8_t* b_resident = smem + (size_t)p.stages * stage_bytes;         // [num_kb][BN x BK] iff p.b_resident
@@ -207,8 +208,10 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
         if (elect_one()) {
             if (p.b_resident) {                  // single N tile: the whole [BN x K] weight matrix, once
                 mbar_expect_tx(wres_bar, (uint32_t)num_kb * b_bytes);
-                for (int kb = 0; kb < num_kb; ++kb)
+                for (int kb = 0; kb < num_kb; ++kb) {
                     tma_load_2d(b_resident + (size_t)kb * b_bytes, &p.tmB, wres_bar, kb * p.BK, 0);
+                    if (p.w_split) tma_load_2d(b_resident + (size_t)kb * b_bytes + b_half, &p.tmB, wres_bar, kb * p.BK, p.cout_pad);
+                }
             } else {
                 int stage = 0;
                 uint32_t phase = 0;
@@ -221,6 +224,8 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                         if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag)) { ok = false; break; }
                         mbar_expect_tx(&full_bar[stage], b_bytes);
                         tma_load_2d(smem + (size_t)stage * stage_bytes + a_bytes, &p.tmB, &full_bar[stage], k0, n0);
+                        if (p.w_split)
+                            tma_load_2d(smem + (size_t)stage * stage_bytes + a_bytes + b_half, &p.tmB, &full_bar[stage], k0, p.cout_pad + n0);
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1u;
@@ -263,8 +268,16 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                     const uint32_t b_addr = p.b_resident ? wres_base + (uint32_t)kb * b_bytes : a_addr + a_bytes;
                     uint64_t da = desc_tmpl | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
                     uint64_t db = desc_tmpl | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
-                    for (int k = 0; k < ksteps; ++k, da += 2, db += 2)      // +32 bytes per K=16 step
-                        umma_bf16(tmem_acc, da, db, p.idesc, (uint32_t)((kb - kb0) | k));
+                    if (!p.w_split) {
+                        for (int k = 0; k < ksteps; ++k, da += 2, db += 2)      // +32 bytes per K=16 step
+                            umma_bf16(tmem_acc, da, db, p.idesc, (uint32_t)((kb - kb0) | k));
+                    } else {                                     // A * (W_hi + W_lo): the small term first
+                        const uint64_t lo_off = (uint64_t)(b_half >> 4);
+                        for (int k = 0; k < ksteps; ++k, da += 2, db += 2) {
+                            umma_bf16(tmem_acc, da, db + lo_off, p.idesc, (uint32_t)((kb - kb0) | k));
+                            umma_bf16(tmem_acc, da, db, p.idesc, 1u);
+                        }
+                    }
                     umma_commit(&empty_bar[stage]);          // frees the stage when the MMAs retire
                     if (++stage == p.stages) {
                         stage = 0;
@@ -290,7 +303,7 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
         };
         auto release = [&](int buf) { mbar_arrive(&acc_empty[buf]); };
         if (p.split_k > 1)
-            conv_epilogue_split<kEpiWarps>(
+            conv_epilogue_split<kEpiWarps, kF16>(
                 p, tmem_base, acc_full, epi_stage, res_full, s_last, warp - kFirstEpiWarp, lane,
                 [&](int local, int& tile, int& slice_k) {
                     const int item = (int)blockIdx.x + local * (int)gridDim.x;
@@ -300,7 +313,7 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                 },
                 origin, release);
         else
-            conv_epilogue<kEpiWarps>(p, tmem_base, acc_full, epi_stage, res_full, warp - kFirstEpiWarp, lane,
+            conv_epilogue<kEpiWarps, kF16>(p, tmem_base, acc_full, epi_stage, res_full, warp - kFirstEpiWarp, lane,
                                      (int)blockIdx.x, (int)gridDim.x, origin, release);
     }
 
@@ -360,7 +373,6 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
     if (!conv_tc_supported(a)) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: unsupported convolution shape");
     launch->patch = 0;
     launch->p.dbg = getenv("RTOD_CLK_DBG") ? 8 : 0;
-    if (!force && conv_patch_eligible(a)) return conv_patch_prepare(a, err_flag, launch);
     if (force ? force->pair == 1 : conv_pair_eligible(a)) {
         if (!conv_pair_eligible(a)) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: CTA-pair kernel not applicable");
         return conv_pair_prepare(a, err_flag, launch);
@@ -410,16 +422,19 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
     int cols = 32;
     while (cols < 2 * BN) cols <<= 1;                    // two accumulator buffers
     p.tmem_cols = cols;
-    // c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major both, N>>3 at 17, M>>4 at 24
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-    const uint32_t stage_bytes = (uint32_t)(kBM + BN) * BK * 2;
+    p.f16 = a.in.f16;
+    p.w_split = a.w_split;
+    p.cout_pad = a.Cout_pad;
+    // c_format F32 (bit 4), a/b format (bits 7, 10: 0 = F16, 1 = BF16), K-major both, N>>3 at 17, M>>4 at 24
+    p.idesc = umma_idesc(p.f16, kBM, BN);
+    const uint32_t stage_bytes = (uint32_t)(kBM + (BN << a.w_split)) * BK * 2;
     p.has_res = a.res != nullptr;
     // ---- shared-memory plan --------------------------------------------------------------------
     // Thin tiles (little MMA work per TMA operation and per epilogue row) run 2-3 CTAs per SM (TMEM:
     // 2*BN columns each) with four epilogue warps each, a single staging slice per warp and no
     // resident weights if that is what makes them fit; fat tiles (BN = 256) keep one CTA per SM,
     // eight epilogue warps and the deepest operand ring that fits.
-    const uint32_t w_bytes = (uint32_t)BN * a.K * 2;
+    const uint32_t w_bytes = (uint32_t)(BN << a.w_split) * a.K * 2;
     const bool may_reside = a.Cout_pad == BN && w_bytes <= kResidentLimit && getenv("RTOD_TC_NO_RESIDENT") == nullptr;
     const uint32_t a_stage = (uint32_t)kBM * BK * 2;
     int max_ctas = 512 / cols;
@@ -515,7 +530,7 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
         const cuuint64_t dims[2] = {(cuuint64_t)a.Cin, (cuuint64_t)M};
         const cuuint64_t strides[1] = {(cuuint64_t)a.in.pitch * 2};
         const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)kBM};
-        r = encode_tiled(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.in.ptr, dims, strides, box, estr1,
+        r = encode_tiled(&p.tmA, h16_tmap_type(a.in.f16), 2, a.in.ptr, dims, strides, box, estr1,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
@@ -527,7 +542,7 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
         const int lower[2] = {-a.pad, -a.pad};
         const int upper[2] = {a.pad - (a.ks - 1), a.pad - (a.ks - 1)};
         const cuuint32_t estr[4] = {1, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1};
-        r = encode_im2col(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.in.ptr, dims, strides, lower, upper,
+        r = encode_im2col(&p.tmA, h16_tmap_type(a.in.f16), 4, a.in.ptr, dims, strides, lower, upper,
                           (cuuint32_t)BK, (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           swizzle_for(BK), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -543,10 +558,10 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
                     a.Cin, a.in.pitch, (int)r);
     // ---- B ----
     {
-        const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.Cout_pad};
+        const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)(a.Cout_pad << a.w_split)};
         const cuuint64_t strides[1] = {(cuuint64_t)a.K * 2};
         const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
-        r = encode_tiled(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.w), dims,
+        r = encode_tiled(&p.tmB, h16_tmap_type(a.in.f16), 2, const_cast<void*>(a.w), dims,
                          strides, box, estr1, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK),
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS)
@@ -556,7 +571,7 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
     // ---- epilogue: output slice store, shortcut operand load (same 32-row x 128-byte box) ----
     {
         const size_t esz = a.out.fp32 ? 4 : 2;
-        const CUtensorMapDataType dt = a.out.fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        const CUtensorMapDataType dt = a.out.fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : h16_tmap_type(a.in.f16);
         const CUtensorMapSwizzle sw = p.ecols * esz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
         const cuuint64_t dims[2] = {(cuuint64_t)a.Cout, (cuuint64_t)M};
         const cuuint64_t strides[1] = {(cuuint64_t)a.out.pitch * esz};
@@ -568,15 +583,18 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
                         a.out.pitch, (int)r);
         if (p.has_res) {
             const cuuint64_t rstrides[1] = {(cuuint64_t)a.res_pitch * 2};
-            r = encode_tiled(&p.tmRes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.res), dims,
+            r = encode_tiled(&p.tmRes, h16_tmap_type(a.in.f16), 2, const_cast<void*>(a.res), dims,
                              rstrides, box, estr1, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS)
                 return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (shortcut operand) failed: %d", (int)r);
         }
     }
-    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // per device and cheap: set on every prepare (a process may drive several GPUs)
+    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return RTOD_OK;
 }
 
@@ -592,7 +610,7 @@ int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cud
             return RTOD_OK;                              // (a candidate that does not fit falls through to the default)
     }
     int rc = conv_tc_prepare(a, err_flag, launch, nullptr);              // heuristic choice = fallback
-    if (rc || launch->patch == 1 || getenv("RTOD_TC_NO_AUTOTUNE")) return rc;
+    if (rc || getenv("RTOD_TC_NO_AUTOTUNE")) return rc;
     cudaEvent_t e0, e1;
     RTOD_CUDA_OK(cudaEventCreate(&e0));
     RTOD_CUDA_OK(cudaEventCreate(&e1));
@@ -649,7 +667,6 @@ int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cud
 
 int conv_tc_launch(const ConvTcLaunch& launch, cudaStream_t stream) {
     if (launch.patch == 2) return conv_pair_launch(launch, stream);
-    if (launch.patch) return conv_patch_launch(launch, stream);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = launch.grid;
     cfg.blockDim = dim3((unsigned)threads_for(launch.p.epi_warps), 1, 1);
@@ -660,8 +677,13 @@ int conv_tc_launch(const ConvTcLaunch& launch, cudaStream_t stream) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    if (launch.p.epi_warps == 8) RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<8>, launch.p));
-    else RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<4>, launch.p));
+    if (launch.p.f16) {
+        if (launch.p.epi_warps == 8) RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<8, true>, launch.p));
+        else RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<4, true>, launch.p));
+    } else {
+        if (launch.p.epi_warps == 8) RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<8, false>, launch.p));
+        else RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<4, false>, launch.p));
+    }
     return RTOD_OK;
 }
 

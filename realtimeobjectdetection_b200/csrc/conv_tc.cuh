@@ -31,31 +31,14 @@ struct alignas(64) ConvTcParams {
     uint32_t idesc;             // tcgen05 instruction descriptor (bf16 x bf16 -> fp32, M=128, N=BN)
     const void* pf_ptr;         // next convolution's weights: prefetched into L2 while this layer runs (small batches)
     unsigned long long pf_bytes;
+    int f16;                    // 16-bit storage type of activations / weights: 1 = fp16, 0 = bf16
+    int w_split;                // 1: weights are hi + lo (two fp16 terms, rows [Cout_pad, 2*Cout_pad) of tmB hold lo):
+                                // two MMAs per K step, for layers whose tensor time hides behind their HBM time
+    int cout_pad;               // row offset of the lo half in tmB
     int split_k, split_shift;   // K slices per output tile (power of two, 1 = off) and log2 of it
     float* split_scratch;       // [total_tiles][split_k][128][BN] fp32 partial accumulators
     int* split_count;           // [total_tiles] arrival counters (zero between forwards)
     uint32_t fd_mtiles[3], fd_wo[3], fd_howo[3];   // FastDiv {mul, shift, d} for m_tiles, Wo, Ho*Wo (tc_ptx.cuh)
-};
-
-// 3x3 / stride 1 / pad 1 convolutions: "halo patch" variant (conv_patch.cu).  One TMA tiled load
-// brings a (TH+2) x (TW+2) pixel patch of a 16/32/64-channel slice; the nine filter taps are nine
-// row-shifted views of that patch (UMMA descriptors may start at any 128-byte row of a swizzled
-// tile), so the activations are fetched once instead of nine times.
-struct alignas(64) ConvPatchParams {
-    CUtensorMap tmA;            // input: 4-D tiled {C, W, H, N}, box {BK, PW, PH, 1}
-    CUtensorMap tmB;            // weights: 2-D tiled {K, Cout_pad}, box {BK, BN}
-    CUtensorMap tmOut;          // output: 4-D tiled {Cout, W, H, N}, box {ecols, TW, TH, 1}
-    CUtensorMap tmRes;          // shortcut operand, same box (valid iff has_res)
-    const float* bias;
-    int* err_flag;
-    int has_res, b_resident, leaky;
-    int ecols, BK, BN, cchunks;
-    int TW, TH, PW, PH;         // output tile, input patch (PW = TW + 2, PH = TH + 2)
-    int tiles_x, tiles_y, m_tiles, total_tiles;
-    int a_bufs, b_stages;       // patch buffers in flight, weight ring depth
-    uint32_t a_buf_bytes;       // one patch buffer (rows 0 .. 128 + 2*PW + 2), 1024-aligned
-    int tmem_cols;
-    uint32_t idesc;
 };
 
 struct ConvTcChoice {           // one launch configuration of conv_tc_kernel (or the CTA-pair kernel)
@@ -68,8 +51,7 @@ struct ConvTcChoice {           // one launch configuration of conv_tc_kernel (o
 struct ConvTcLaunch {           // host side: kernel parameters + launch geometry
     ConvTcChoice choice;
     ConvTcParams p;
-    ConvPatchParams pp;
-    int patch;                  // 0: conv_tc_kernel(p), 1: conv_patch_kernel(pp), 2: conv_pair_kernel(p)
+    int patch;                  // 0: conv_tc_kernel(p), 2: conv_pair_kernel(p)
     dim3 grid;
     uint32_t smem_bytes;
 };
@@ -78,11 +60,6 @@ struct ConvTcLaunch {           // host side: kernel parameters + launch geometr
 bool conv_pair_eligible(const ConvArgs& a);
 int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch);
 int conv_pair_launch(const ConvTcLaunch& launch, cudaStream_t stream);
-
-// conv_patch.cu
-bool conv_patch_eligible(const ConvArgs& a);
-int conv_patch_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch);
-int conv_patch_launch(const ConvTcLaunch& launch, cudaStream_t stream);
 
 // K slices per output tile for this shape (1 = none); deterministic
 int conv_split_factor(const ConvArgs& a);

@@ -1,8 +1,8 @@
-// layers.cu -- the non-GEMM layers of Darknet.forward (src/darknet.py:199-295) on NHWC bf16
-// activations: stem convolution (Cin = 3, fused NCHW fp32 -> NHWC bf16), max-pool
+// layers.cu -- the non-GEMM layers of Darknet.forward (src/darknet.py:199-295) on NHWC fp16/bf16
+// activations: stem convolution (Cin = 3, fused NCHW fp32 -> NHWC 16-bit), max-pool
 // (src/darknet.py:17-46, 547-555), bilinear x2 upsample (src/darknet.py:591-592), the
 // copy/add fall-backs for route/shortcut (src/darknet.py:263-290) when they cannot be fused
-// into a convolution, and the weight ingest (BatchNorm fold + K-major bf16 re-layout,
+// into a convolution, and the weight ingest (BatchNorm fold + K-major fp16/bf16 re-layout,
 // src/darknet.py:316-410).  All of them are HBM-bound: 16-byte vector accesses, one pass.
 #include "layers.cuh"
 
@@ -14,9 +14,33 @@ namespace {
 
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
+template <bool kF16> __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+    if constexpr (kF16) {
+        const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+        return *reinterpret_cast<const uint32_t*>(&r);
+    } else {
+        const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+        return *reinterpret_cast<const uint32_t*>(&r);
+    }
+}
+
+// warp-level tensor-core step D += A(16x16) * B(16x8), fp32 accumulate, fp16 or bf16 operands
+template <bool kF16>
+__device__ __forceinline__ void mma_m16n8k16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    if constexpr (kF16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 // ---------------------------------------------------------------------------------------------
 // stem: 3x3 convolution over a 3-channel NCHW fp32 image, bias + leaky fused, NHWC bf16 out
 // ---------------------------------------------------------------------------------------------
+template <bool kF16>
 __global__ void __launch_bounds__(128)
 stem_conv3x3_kernel(const float* __restrict__ x, int B, int H, int W, const float* __restrict__ w,
                     const float* __restrict__ bias, int Cout, int stride, int pad, int leaky, Act out) {
@@ -41,7 +65,7 @@ stem_conv3x3_kernel(const float* __restrict__ x, int B, int H, int W, const floa
                         ? __ldg(x + (((long long)b * 3 + c) * H + iy) * W + ix)
                         : 0.0f;
             }
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out.ptr) + pix * out.pitch;
+    unsigned short* dst = reinterpret_cast<unsigned short*>(out.ptr) + pix * out.pitch;
     for (int n0 = 0; n0 < Cout; n0 += 8) {
         float acc[8];
 #pragma unroll
@@ -54,10 +78,10 @@ stem_conv3x3_kernel(const float* __restrict__ x, int B, int H, int W, const floa
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = leaky01(acc[j]);
         uint4 v;
-        v.x = pack_bf16x2(acc[0], acc[1]);
-        v.y = pack_bf16x2(acc[2], acc[3]);
-        v.z = pack_bf16x2(acc[4], acc[5]);
-        v.w = pack_bf16x2(acc[6], acc[7]);
+        v.x = pack_h2<kF16>(acc[0], acc[1]);
+        v.y = pack_h2<kF16>(acc[2], acc[3]);
+        v.z = pack_h2<kF16>(acc[4], acc[5]);
+        v.w = pack_h2<kF16>(acc[6], acc[7]);
         *reinterpret_cast<uint4*>(dst + n0) = v;
     }
 }
@@ -71,7 +95,7 @@ stem_conv3x3_kernel(const float* __restrict__ x, int B, int H, int W, const floa
 // fp32-accurate) and stores bf16 NHWC.  The gather of the next tile is issued before the MMAs of
 // the current one.  NT = Cout / 8.
 // ---------------------------------------------------------------------------------------------
-template <int NT>
+template <int NT, bool kF16>
 __global__ void __launch_bounds__(128)
 stem_conv3x3_mma_kernel(const float* __restrict__ x, int B, int H, int W, const float* __restrict__ w,
                         const float* __restrict__ bias, int stride, int pad, int leaky, Act out) {
@@ -99,9 +123,8 @@ stem_conv3x3_mma_kernel(const float* __restrict__ x, int B, int H, int W, const 
                 const int k0 = 16 * s + 2 * t + 8 * hh;
                 const float w0 = k0 < 27 ? __ldg(w + (8 * j + g) * 27 + k0) : 0.0f;
                 const float w1 = k0 + 1 < 27 ? __ldg(w + (8 * j + g) * 27 + k0 + 1) : 0.0f;
-                const float h0 = __bfloat162float(__float2bfloat16_rn(w0)), h1 = __bfloat162float(__float2bfloat16_rn(w1));
-                bhi[j][s][hh] = pack_bf16x2(h0, h1);
-                blo[j][s][hh] = pack_bf16x2(w0 - h0, w1 - h1);
+                bhi[j][s][hh] = pack_h2<kF16>(w0, w1);
+                blo[j][s][hh] = pack_h2<kF16>(w0 - h2_lo<kF16>(bhi[j][s][hh]), w1 - h2_hi<kF16>(bhi[j][s][hh]));
             }
     float bia[NT][2];
 #pragma unroll
@@ -114,7 +137,7 @@ stem_conv3x3_mma_kernel(const float* __restrict__ x, int B, int H, int W, const 
     const long long P = (long long)B * Ho * Wo;
     const long long n_tiles = (P + 15) / 16;
     const long long warps = (long long)gridDim.x * 4;
-    __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(out.ptr);
+    unsigned short* obase = reinterpret_cast<unsigned short*>(out.ptr);
 
     auto gather = [&](long long tile, float (&v)[16]) {     // rows g and g + 8 of the tile, 8 taps each
 #pragma unroll
@@ -146,10 +169,9 @@ stem_conv3x3_mma_kernel(const float* __restrict__ x, int B, int H, int W, const 
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const float v0 = cur[rr * 8 + s * 4 + hh * 2], v1 = cur[rr * 8 + s * 4 + hh * 2 + 1];
-                    const float h0 = __bfloat162float(__float2bfloat16_rn(v0));
-                    const float h1 = __bfloat162float(__float2bfloat16_rn(v1));
-                    ahi[s][hh * 2 + rr] = pack_bf16x2(h0, h1);
-                    alo[s][hh * 2 + rr] = pack_bf16x2(v0 - h0, v1 - h1);
+                    const uint32_t hi = pack_h2<kF16>(v0, v1);
+                    ahi[s][hh * 2 + rr] = hi;
+                    alo[s][hh * 2 + rr] = pack_h2<kF16>(v0 - h2_lo<kF16>(hi), v1 - h2_hi<kF16>(hi));
                 }
         float acc[NT][4];
 #pragma unroll
@@ -157,11 +179,7 @@ stem_conv3x3_mma_kernel(const float* __restrict__ x, int B, int H, int W, const 
             acc[j][0] = bia[j][0]; acc[j][1] = bia[j][1]; acc[j][2] = bia[j][0]; acc[j][3] = bia[j][1];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-#define RTOD_MMA(A, Bf)                                                                                      \
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, " \
-                 "{%0,%1,%2,%3};"                                                                            \
-                 : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])                        \
-                 : "r"(A[s][0]), "r"(A[s][1]), "r"(A[s][2]), "r"(A[s][3]), "r"(Bf[j][s][0]), "r"(Bf[j][s][1]))
+#define RTOD_MMA(A, Bf) mma_m16n8k16<kF16>(acc[j], A[s], Bf[j][s])
                 RTOD_MMA(alo, bhi);
                 RTOD_MMA(ahi, blo);
                 RTOD_MMA(ahi, bhi);
@@ -172,7 +190,7 @@ stem_conv3x3_mma_kernel(const float* __restrict__ x, int B, int H, int W, const 
         for (int rr = 0; rr < 2; ++rr) {
             const long long pix = tile * 16 + g + 8 * rr;
             if (pix >= P) continue;
-            __nv_bfloat16* dst = obase + pix * out.pitch + 2 * t;
+            unsigned short* dst = obase + pix * out.pitch + 2 * t;
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 float v0 = acc[j][2 * rr], v1 = acc[j][2 * rr + 1];
@@ -180,7 +198,7 @@ stem_conv3x3_mma_kernel(const float* __restrict__ x, int B, int H, int W, const 
                     v0 = leaky01(v0);
                     v1 = leaky01(v1);
                 }
-                *reinterpret_cast<uint32_t*>(dst + 8 * j) = pack_bf16x2(v0, v1);
+                *reinterpret_cast<uint32_t*>(dst + 8 * j) = pack_h2<kF16>(v0, v1);
             }
         }
 #pragma unroll
@@ -191,6 +209,7 @@ stem_conv3x3_mma_kernel(const float* __restrict__ x, int B, int H, int W, const 
 // ---------------------------------------------------------------------------------------------
 // layout converters (plan input when the first layer is not a stem; debug read-back)
 // ---------------------------------------------------------------------------------------------
+template <bool kF16>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, Act out) {
     const int HW = out.H * out.W, groups = out.C / 8;
     const long long total = (long long)B * HW * groups;
@@ -204,15 +223,16 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, Act out)
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (long long)j * HW);
         uint4 o;
-        o.x = pack_bf16x2(v[0], v[1]);
-        o.y = pack_bf16x2(v[2], v[3]);
-        o.z = pack_bf16x2(v[4], v[5]);
-        o.w = pack_bf16x2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out.ptr) +
+        o.x = pack_h2<kF16>(v[0], v[1]);
+        o.y = pack_h2<kF16>(v[2], v[3]);
+        o.z = pack_h2<kF16>(v[4], v[5]);
+        o.w = pack_h2<kF16>(v[6], v[7]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(out.ptr) +
                                   ((long long)b * HW + p) * out.pitch + g * 8) = o;
     }
 }
 
+template <bool kF16>
 __global__ void nhwc_to_nchw_kernel(Act in, int B, float* __restrict__ out) {
     const int HW = in.H * in.W;
     const long long total = (long long)B * in.C * HW;
@@ -223,7 +243,7 @@ __global__ void nhwc_to_nchw_kernel(Act in, int B, float* __restrict__ out) {
         const int b = (int)(i / ((long long)HW * in.C));
         const long long src = ((long long)b * HW + p) * in.pitch + c;
         out[i] = in.fp32 ? reinterpret_cast<const float*>(in.ptr)[src]
-                         : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in.ptr)[src]);
+                         : h1_to_float<kF16>(reinterpret_cast<const unsigned short*>(in.ptr)[src]);
     }
 }
 
@@ -231,7 +251,7 @@ __global__ void nhwc_to_nchw_kernel(Act in, int B, float* __restrict__ out) {
 // max-pool: MaxPool2d(size, stride) (floor mode, no padding) or, for stride 1, the reference's
 // MaxPoolStride1: replicate-pad right/bottom by size-1, then pool with stride size-1
 // ---------------------------------------------------------------------------------------------
-template <typename Index>                                   // 32-bit index arithmetic where the tensor allows
+template <typename Index, bool kF16>                        // 32-bit index arithmetic where the tensor allows
 __global__ void maxpool_kernel(Act in, Act out, int B, int size, int step, int clamp_edge) {
     const int groups = out.C / 8;
     const Index total = (Index)B * out.H * out.W * groups;
@@ -242,8 +262,8 @@ __global__ void maxpool_kernel(Act in, Act out, int B, int size, int step, int c
         const int ox = (int)(pix - line * (Index)out.W);
         const int b = (int)(line / (Index)out.H);
         const int oy = (int)(line - (Index)b * (Index)out.H);
-        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(in.ptr) + g * 8;
-        __nv_bfloat162 best[4];
+        const unsigned short* base = reinterpret_cast<const unsigned short*>(in.ptr) + g * 8;
+        uint32_t best[4];
         bool first = true;
         for (int dy = 0; dy < size; ++dy) {
             int iy = oy * step + dy;
@@ -258,20 +278,20 @@ __global__ void maxpool_kernel(Act in, Act out, int B, int size, int step, int c
                     ix = in.W - 1;
                 }
                 const uint4 v = ldg16(base + (((long long)b * in.H + iy) * in.W + ix) * in.pitch);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+                const uint32_t* h = &v.x;
                 if (first) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) best[j] = h[j];
                     first = false;
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) best[j] = __hmax2(best[j], h[j]);
+                    for (int j = 0; j < 4; ++j) best[j] = hmax2_u32<kF16>(best[j], h[j]);
                 }
             }
         }
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out.ptr) +
+        *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(out.ptr) +
                                   (((long long)b * out.H + oy) * out.W + ox) * out.pitch + g * 8) =
-            *reinterpret_cast<uint4*>(best);
+            make_uint4(best[0], best[1], best[2], best[3]);
     }
 }
 
@@ -280,7 +300,7 @@ __global__ void maxpool_kernel(Act in, Act out, int B, int size, int step, int c
 // indices clamped at the border; evaluated like ATen: h0*(w0*a + w1*b) + h1*(w0*c + w1*d)
 // ---------------------------------------------------------------------------------------------
 // Index: 32-bit where the tensor allows (64-bit divides cost ~100 instructions each; the kernel was issue-bound)
-template <typename Index>
+template <typename Index, bool kF16>
 __global__ void upsample2x_kernel(Act in, Act out, int B) {
     const int groups = out.C / 8;
     const Index total = (Index)B * out.H * out.W * groups;
@@ -295,7 +315,7 @@ __global__ void upsample2x_kernel(Act in, Act out, int B) {
         const int y0 = (int)sy, x0 = (int)sx;
         const int y1 = min(y0 + 1, in.H - 1), x1 = min(x0 + 1, in.W - 1);
         const float hy1 = sy - y0, hy0 = 1.0f - hy1, wx1 = sx - x0, wx0 = 1.0f - wx1;
-        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(in.ptr) + g * 8;
+        const unsigned short* base = reinterpret_cast<const unsigned short*>(in.ptr) + g * 8;
         const long long row0 = ((long long)b * in.H + y0) * in.W, row1 = ((long long)b * in.H + y1) * in.W;
         const uint4 a = ldg16(base + (row0 + x0) * in.pitch), bb = ldg16(base + (row0 + x1) * in.pitch);
         const uint4 c = ldg16(base + (row1 + x0) * in.pitch), d = ldg16(base + (row1 + x1) * in.pitch);
@@ -304,13 +324,13 @@ __global__ void upsample2x_kernel(Act in, Act out, int B) {
         uint32_t* po = &o.x;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float lo = hy0 * (wx0 * bf16_lo(pa[j]) + wx1 * bf16_lo(pb[j])) +
-                             hy1 * (wx0 * bf16_lo(pc[j]) + wx1 * bf16_lo(pd[j]));
-            const float hi = hy0 * (wx0 * bf16_hi(pa[j]) + wx1 * bf16_hi(pb[j])) +
-                             hy1 * (wx0 * bf16_hi(pc[j]) + wx1 * bf16_hi(pd[j]));
-            po[j] = pack_bf16x2(lo, hi);
+            const float lo = hy0 * (wx0 * h2_lo<kF16>(pa[j]) + wx1 * h2_lo<kF16>(pb[j])) +
+                             hy1 * (wx0 * h2_lo<kF16>(pc[j]) + wx1 * h2_lo<kF16>(pd[j]));
+            const float hi = hy0 * (wx0 * h2_hi<kF16>(pa[j]) + wx1 * h2_hi<kF16>(pb[j])) +
+                             hy1 * (wx0 * h2_hi<kF16>(pc[j]) + wx1 * h2_hi<kF16>(pd[j]));
+            po[j] = pack_h2<kF16>(lo, hi);
         }
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out.ptr) +
+        *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(out.ptr) +
                                   (((long long)b * out.H + oy) * out.W + ox) * out.pitch + g * 8) = o;
     }
 }
@@ -322,11 +342,12 @@ __global__ void copy_kernel(Act in, Act out, int B) {
          i += (long long)gridDim.x * blockDim.x) {
         const int g = (int)(i % groups);
         const long long p = i / groups;
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out.ptr) + p * out.pitch + g * 8) =
-            ldg16(reinterpret_cast<const __nv_bfloat16*>(in.ptr) + p * in.pitch + g * 8);
+        *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(out.ptr) + p * out.pitch + g * 8) =
+            ldg16(reinterpret_cast<const unsigned short*>(in.ptr) + p * in.pitch + g * 8);
     }
 }
 
+template <bool kF16>
 __global__ void add_kernel(Act a, Act b, Act out, int B) {
     const int groups = out.C / 8;
     const long long total = (long long)B * out.H * out.W * groups;
@@ -334,26 +355,28 @@ __global__ void add_kernel(Act a, Act b, Act out, int B) {
          i += (long long)gridDim.x * blockDim.x) {
         const int g = (int)(i % groups);
         const long long p = i / groups;
-        const uint4 va = ldg16(reinterpret_cast<const __nv_bfloat16*>(a.ptr) + p * a.pitch + g * 8);
-        const uint4 vb = ldg16(reinterpret_cast<const __nv_bfloat16*>(b.ptr) + p * b.pitch + g * 8);
+        const uint4 va = ldg16(reinterpret_cast<const unsigned short*>(a.ptr) + p * a.pitch + g * 8);
+        const uint4 vb = ldg16(reinterpret_cast<const unsigned short*>(b.ptr) + p * b.pitch + g * 8);
         const uint32_t* pa = &va.x; const uint32_t* pb = &vb.x;
         uint4 o;
         uint32_t* po = &o.x;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            po[j] = pack_bf16x2(bf16_lo(pa[j]) + bf16_lo(pb[j]), bf16_hi(pa[j]) + bf16_hi(pb[j]));
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out.ptr) + p * out.pitch + g * 8) = o;
+            po[j] = pack_h2<kF16>(h2_lo<kF16>(pa[j]) + h2_lo<kF16>(pb[j]), h2_hi<kF16>(pa[j]) + h2_hi<kF16>(pb[j]));
+        *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(out.ptr) + p * out.pitch + g * 8) = o;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // weight ingest: BatchNorm fold (eval semantics) + [Cout,Cin,k,k] fp32 -> [Cout][(ky,kx,c)] bf16
 // ---------------------------------------------------------------------------------------------
+template <bool kF16>
 __global__ void fold_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ mean, const float* __restrict__ var,
-                                 float eps, int Cout, int Cin, int ks, __nv_bfloat16* __restrict__ wp,
-                                 float* __restrict__ wf, float* __restrict__ bias_out) {
+                                 float eps, int Cout, int Cin, int ks, int Cout_pad, int w_split,
+                                 unsigned short* __restrict__ wp, float* __restrict__ wf,
+                                 float* __restrict__ bias_out) {
     const int K = Cin * ks * ks;
     const long long total = (long long)Cout * K;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -362,7 +385,10 @@ __global__ void fold_pack_kernel(const float* __restrict__ w, const float* __res
         const int c = r / (ks * ks), t = r % (ks * ks);
         const float scale = gamma ? gamma[o] * (1.0f / sqrtf(var[o] + eps)) : 1.0f;
         const float v = w[i] * scale;
-        wp[(long long)o * K + (long long)t * Cin + c] = __float2bfloat16_rn(v);
+        const unsigned short hi = float_to_h1<kF16>(v);
+        wp[(long long)o * K + (long long)t * Cin + c] = hi;
+        if (w_split)                                         // second term of the two-term weight (rows Cout_pad ..)
+            wp[(long long)(Cout_pad + o) * K + (long long)t * Cin + c] = float_to_h1<kF16>(v - h1_to_float<kF16>(hi));
         if (wf) wf[i] = v;
         if (r == 0) {
             float bv = bias ? bias[o] : 0.0f;
@@ -393,15 +419,21 @@ int launch_stem_conv(const float* x, int B, int Cin, int H, int W, const float* 
     const long long pixels = (long long)B * out.H * out.W;
     long long blocks = (pixels + 63) / 64;                       // 4 warps x 16 pixels per pass
     if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
-    if (Cout == 32)
-        stem_conv3x3_mma_kernel<4><<<(unsigned)blocks, 128, 0, stream>>>(x, B, H, W, w, bias, stride, pad, leaky, out);
-    else if (Cout == 16)
-        stem_conv3x3_mma_kernel<2><<<(unsigned)blocks, 128, 0, stream>>>(x, B, H, W, w, bias, stride, pad, leaky, out);
-    else if (Cout == 64)
-        stem_conv3x3_mma_kernel<8><<<(unsigned)blocks, 128, 0, stream>>>(x, B, H, W, w, bias, stride, pad, leaky, out);
-    else
-        stem_conv3x3_kernel<<<ceil_div(pixels, 128), 128, (size_t)Cout * 28 * sizeof(float), stream>>>(
+#define RTOD_STEM_MMA(NT)                                                                                              \
+    do {                                                                                                               \
+        if (out.f16) stem_conv3x3_mma_kernel<NT, true><<<(unsigned)blocks, 128, 0, stream>>>(x, B, H, W, w, bias, stride, pad, leaky, out);  \
+        else stem_conv3x3_mma_kernel<NT, false><<<(unsigned)blocks, 128, 0, stream>>>(x, B, H, W, w, bias, stride, pad, leaky, out);         \
+    } while (0)
+    if (Cout == 32) RTOD_STEM_MMA(4);
+    else if (Cout == 16) RTOD_STEM_MMA(2);
+    else if (Cout == 64) RTOD_STEM_MMA(8);
+    else if (out.f16)
+        stem_conv3x3_kernel<true><<<ceil_div(pixels, 128), 128, (size_t)Cout * 28 * sizeof(float), stream>>>(
             x, B, H, W, w, bias, Cout, stride, pad, leaky, out);
+    else
+        stem_conv3x3_kernel<false><<<ceil_div(pixels, 128), 128, (size_t)Cout * 28 * sizeof(float), stream>>>(
+            x, B, H, W, w, bias, Cout, stride, pad, leaky, out);
+#undef RTOD_STEM_MMA
     RTOD_LAUNCH_OK("stem_conv3x3 kernel");
     return RTOD_OK;
 }
@@ -409,41 +441,51 @@ int launch_stem_conv(const float* x, int B, int Cin, int H, int W, const float* 
 int launch_nchw_to_nhwc(const float* x, int B, Act out, cudaStream_t stream) {
     if (out.C % 8 != 0 || out.fp32) return fail(RTOD_ERR_UNSUPPORTED, "input channels must be a multiple of 8");
     const long long total = (long long)B * out.H * out.W * (out.C / 8);
-    nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, B, out);
+    if (out.f16) nchw_to_nhwc_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(x, B, out);
+    else nchw_to_nhwc_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(x, B, out);
     RTOD_LAUNCH_OK("nchw_to_nhwc_kernel");
     return RTOD_OK;
 }
 
 int launch_nhwc_to_nchw(Act in, int B, float* out, cudaStream_t stream) {
     const long long total = (long long)B * in.C * in.H * in.W;
-    nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, B, out);
+    if (in.f16) nhwc_to_nchw_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(in, B, out);
+    else nhwc_to_nchw_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(in, B, out);
     RTOD_LAUNCH_OK("nhwc_to_nchw_kernel");
     return RTOD_OK;
 }
 
+#define RTOD_BY_INDEX_AND_TYPE(kernel, total, f16, ...)                                                        \
+    do {                                                                                                       \
+        if ((total) < (1ll << 31)) {                                                                           \
+            if (f16) kernel<unsigned, true><<<grid_for(total, 256), 256, 0, stream>>>(__VA_ARGS__);            \
+            else kernel<unsigned, false><<<grid_for(total, 256), 256, 0, stream>>>(__VA_ARGS__);               \
+        } else {                                                                                               \
+            if (f16) kernel<long long, true><<<grid_for(total, 256), 256, 0, stream>>>(__VA_ARGS__);           \
+            else kernel<long long, false><<<grid_for(total, 256), 256, 0, stream>>>(__VA_ARGS__);              \
+        }                                                                                                      \
+    } while (0)
+
 int launch_maxpool(Act in, Act out, int B, int size, int stride, cudaStream_t stream) {
-    if (in.C % 8 != 0 || in.fp32 || out.fp32) return fail(RTOD_ERR_UNSUPPORTED, "maxpool needs bf16, C%%8==0");
+    if (in.C % 8 != 0 || in.fp32 || out.fp32) return fail(RTOD_ERR_UNSUPPORTED, "maxpool needs 16-bit activations, C%%8==0");
     const long long total = (long long)B * out.H * out.W * (out.C / 8);
     const int step = stride != 1 ? stride : size - 1;           // src/darknet.py:35,45
-    if (total < (1ll << 31))
-        maxpool_kernel<unsigned><<<grid_for(total, 256), 256, 0, stream>>>(in, out, B, size, step < 1 ? 1 : step, stride == 1);
-    else
-        maxpool_kernel<long long><<<grid_for(total, 256), 256, 0, stream>>>(in, out, B, size, step < 1 ? 1 : step, stride == 1);
+    RTOD_BY_INDEX_AND_TYPE(maxpool_kernel, total, in.f16, in, out, B, size, step < 1 ? 1 : step, stride == 1);
     RTOD_LAUNCH_OK("maxpool_kernel");
     return RTOD_OK;
 }
 
 int launch_upsample2x(Act in, Act out, int B, cudaStream_t stream) {
-    if (in.C % 8 != 0 || in.fp32 || out.fp32) return fail(RTOD_ERR_UNSUPPORTED, "upsample needs bf16, C%%8==0");
+    if (in.C % 8 != 0 || in.fp32 || out.fp32) return fail(RTOD_ERR_UNSUPPORTED, "upsample needs 16-bit activations, C%%8==0");
     const long long total = (long long)B * out.H * out.W * (out.C / 8);
-    if (total < (1ll << 31)) upsample2x_kernel<unsigned><<<grid_for(total, 256), 256, 0, stream>>>(in, out, B);
-    else upsample2x_kernel<long long><<<grid_for(total, 256), 256, 0, stream>>>(in, out, B);
+    RTOD_BY_INDEX_AND_TYPE(upsample2x_kernel, total, in.f16, in, out, B);
     RTOD_LAUNCH_OK("upsample2x_kernel");
     return RTOD_OK;
 }
+#undef RTOD_BY_INDEX_AND_TYPE
 
 int launch_copy(Act in, Act out, int B, cudaStream_t stream) {
-    if (in.C % 8 != 0 || in.fp32 || out.fp32) return fail(RTOD_ERR_UNSUPPORTED, "copy needs bf16, C%%8==0");
+    if (in.C % 8 != 0 || in.fp32 || out.fp32) return fail(RTOD_ERR_UNSUPPORTED, "copy needs 16-bit activations, C%%8==0");
     const long long total = (long long)B * out.H * out.W * (out.C / 8);
     copy_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, out, B);
     RTOD_LAUNCH_OK("copy_kernel");
@@ -452,19 +494,26 @@ int launch_copy(Act in, Act out, int B, cudaStream_t stream) {
 
 int launch_add(Act a, Act b, Act out, int B, cudaStream_t stream) {
     if (out.C % 8 != 0 || a.fp32 || b.fp32 || out.fp32)
-        return fail(RTOD_ERR_UNSUPPORTED, "shortcut add needs bf16, C%%8==0");
+        return fail(RTOD_ERR_UNSUPPORTED, "shortcut add needs 16-bit activations, C%%8==0");
     const long long total = (long long)B * out.H * out.W * (out.C / 8);
-    add_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a, b, out, B);
+    if (out.f16) add_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(a, b, out, B);
+    else add_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(a, b, out, B);
     RTOD_LAUNCH_OK("add_kernel");
     return RTOD_OK;
 }
 
 int launch_fold_pack(const float* w, const float* bias, const float* gamma, const float* beta,
                      const float* mean, const float* var, float eps, int Cout, int Cin, int ks,
-                     __nv_bfloat16* wp, float* wf, float* bias_out, cudaStream_t stream) {
+                     int Cout_pad, int f16, int w_split, void* wp, float* wf, float* bias_out,
+                     cudaStream_t stream) {
     const long long total = (long long)Cout * Cin * ks * ks;
-    fold_pack_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, bias, gamma, beta, mean, var, eps,
-                                                               Cout, Cin, ks, wp, wf, bias_out);
+    unsigned short* wp16 = static_cast<unsigned short*>(wp);
+    if (f16)
+        fold_pack_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(w, bias, gamma, beta, mean, var, eps, Cout, Cin, ks,
+                                                                         Cout_pad, w_split, wp16, wf, bias_out);
+    else
+        fold_pack_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(w, bias, gamma, beta, mean, var, eps, Cout, Cin, ks,
+                                                                          Cout_pad, w_split, wp16, wf, bias_out);
     RTOD_LAUNCH_OK("fold_pack_kernel");
     return RTOD_OK;
 }

@@ -12,16 +12,18 @@ struct Act {
     void* ptr;
     int C, pitch, H, W;
     int fp32;
+    int f16;                    // 16-bit elements are fp16 (1) or bf16 (0); ignored when fp32
 };
 
 struct ConvArgs {
     Act in, out;
-    const __nv_bfloat16* w;     // [Cout_pad][K] K-major bf16, K = (ky*ks + kx)*Cin + c, BN folded
+    const void* w;              // [Cout_pad][K] K-major fp16/bf16, K = (ky*ks + kx)*Cin + c, BN folded
     const float* bias;          // [Cout_pad] fp32 (BN folded)
-    const __nv_bfloat16* res;   // optional shortcut operand, same pixels/channels as out
+    const void* res;            // optional shortcut operand, same pixels/channels as out
     int res_pitch;
     int B, Cin, Cout, Cout_pad, ks, stride, pad, leaky;
     int K;                      // ks*ks*Cin
+    int w_split;                // weights stored as hi rows [0, Cout_pad) + lo rows [Cout_pad, 2*Cout_pad)
     float* split_scratch;       // split-K scratch shared by all layers of a plan (or null)
     size_t split_scratch_bytes;
     int* split_count;           // zeroed counters, split_count_n entries
@@ -42,8 +44,8 @@ int launch_add(Act a, Act b, Act out, int B, cudaStream_t stream);
 // BN fold + K-major bf16 re-layout (and the fp32 [Cout][Cin*ks*ks] copy the stem kernel reads)
 int launch_fold_pack(const float* w, const float* bias, const float* gamma, const float* beta,
                      const float* mean, const float* var, float eps, int Cout, int Cin, int ks,
-                     __nv_bfloat16* w_packed, float* w_f32_or_null, float* bias_out,
-                     cudaStream_t stream);
+                     int Cout_pad, int f16, int w_split, void* w_packed, float* w_f32_or_null,
+                     float* bias_out, cudaStream_t stream);
 int launch_conv_simt(const ConvArgs& a, cudaStream_t stream);
 
 }  // namespace rtod

@@ -15,6 +15,7 @@
 // (__fadd_rn/__fsub_rn/__fmul_rn/__fdiv_rn): the reference evaluates every tensor op with a
 // separate rounding, so fused multiply-add contraction must not happen here.
 #include "common.cuh"
+#include "iou.cuh"
 
 #include <cstdlib>
 
@@ -30,31 +31,6 @@ constexpr int kScanStages = 3;
 constexpr int kImageThreads = 1024;
 constexpr int kSortSmemCap = 16384;          // keys sortable in shared memory per image (heavy pass)
 constexpr int kLightCap = 4096;              // ... in the light pass
-
-// ---- exact-reference arithmetic -----------------------------------------------------------
-__device__ __forceinline__ float nan_max(float a, float b) {   // torch.max propagates NaN
-    return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b);
-}
-__device__ __forceinline__ float nan_min(float a, float b) {
-    return (a != a || b != b) ? __int_as_float(0x7fc00000) : fminf(a, b);
-}
-__device__ __forceinline__ float clamp_min0(float v) {         // torch.clamp(min=0) keeps NaN
-    return (v != v) ? v : fmaxf(v, 0.0f);
-}
-__device__ __forceinline__ float box_area(float x1, float y1, float x2, float y2) {
-    return __fmul_rn(__fadd_rn(__fsub_rn(x2, x1), 1.0f), __fadd_rn(__fsub_rn(y2, y1), 1.0f));
-}
-// src/util.py:138-151
-__device__ __forceinline__ float iou_exact(float ax1, float ay1, float ax2, float ay2, float aarea,
-                                           float bx1, float by1, float bx2, float by2,
-                                           float barea) {
-    const float left = nan_max(ax1, bx1), top = nan_max(ay1, by1);
-    const float right = nan_min(ax2, bx2), bottom = nan_min(ay2, by2);
-    const float iw = clamp_min0(__fadd_rn(__fsub_rn(right, left), 1.0f));
-    const float ih = clamp_min0(__fadd_rn(__fsub_rn(bottom, top), 1.0f));
-    const float inter = __fmul_rn(iw, ih);
-    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter));
-}
 
 struct Box {
     float x1, y1, x2, y2, area;
@@ -674,12 +650,9 @@ extern "C" int rtod_write_results(const float* pred, int B, int N, int C, float 
     if (const char* e = getenv("RTOD_NMS_DBG")) use_bulk |= atoi(e) << 1;
     const size_t stage_bytes = (size_t)(((rows_per_chunk * L + 31) / 32) * 32) * 4;
     const size_t scan_smem = kScanStages * stage_bytes;
-    static bool scan_attr_set = false;
-    if (!scan_attr_set) {
-        RTOD_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          kScanStages * (kScanStageBytes + 128)));
-        scan_attr_set = true;
-    }
+    // per device (a process may drive several GPUs) and cheap: set on every call
+    RTOD_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kScanStages * (kScanStageBytes + 128)));
     const long long total_rows = (long long)B * N;
     const long long n_chunks = (total_rows + rows_per_chunk - 1) / rows_per_chunk;
     int per_sm = (int)(200 * 1024 / (scan_smem + 1024));
@@ -693,12 +666,8 @@ extern "C" int rtod_write_results(const float* pred, int B, int N, int C, float 
     RTOD_LAUNCH_OK("nms_scan_kernel");
 
     // ---- per-image sort + suppression ---------------------------------------------------
-    static bool image_attr_set = false;
-    if (!image_attr_set) {
-        RTOD_CUDA_OK(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          kSortSmemCap * 12 + kSortSmemCap / 8));
-        image_attr_set = true;
-    }
+    RTOD_CUDA_OK(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kSortSmemCap * 12 + kSortSmemCap / 8));
     {   // light pass: images with at most kLightCap candidates (and the empty ones)
         const int cap = lay.P < kLightCap ? lay.P : kLightCap;
         cudaLaunchAttribute pdl[1];

@@ -42,6 +42,7 @@ struct Node {                            // one cfg block
     // convolution
     int Cin = 0, Cout_pad = 0, K = 0;
     bool stem = false, head = false, use_tc = false, weights_set = false;
+    int w_split = 0;                     // weights kept as hi + lo (two MMAs per K step), see choose_w_split
     int res_src = -2;                    // fused shortcut operand (layer index) or -2
     size_t w_off = 0, wf_off = 0, bias_off = 0;
     ConvArgs args{};
@@ -57,12 +58,14 @@ struct RtodPlan {
     std::vector<rtod::Buf> bufs;
     int batch = 0, in_c = 0, in_h = 0, in_w = 0, inp_dim = 0;
     unsigned flags = 0;
+    int f16 = 1;                         // 16-bit storage type: fp16 (default) or bf16 (RTOD_PLAN_BF16)
     int input_buf = -1;                  // NHWC copy of the input when layer 0 is not a stem conv
     size_t workspace_bytes = 0, weight_bytes = 0;
     size_t split_off = 0;                // offset of the split-K scratch inside the workspace
     unsigned char* ws = nullptr;
     unsigned char* wa = nullptr;
     int* err_flag = nullptr;
+    int* err_sink = nullptr;             // device view of the caller's pinned failure int (or null)
     bool bound = false;
     // decode
     rtod::DecodeHeads heads{};
@@ -86,7 +89,7 @@ Act act_of(const RtodPlan& p, int i) {
     if (i == kInputLayer) {
         const Buf& b = p.bufs[p.input_buf];
         a.ptr = p.ws ? p.ws + b.offset : nullptr;
-        a.C = p.in_c; a.pitch = b.pitch; a.H = p.in_h; a.W = p.in_w; a.fp32 = 0;
+        a.C = p.in_c; a.pitch = b.pitch; a.H = p.in_h; a.W = p.in_w; a.fp32 = 0; a.f16 = p.f16;
         return a;
     }
     const Node& n = p.nodes[i];
@@ -96,7 +99,7 @@ Act act_of(const RtodPlan& p, int i) {
     const Buf& b = p.bufs[rn.buf];
     const size_t esz = b.fp32 ? 4 : 2;
     a.ptr = p.ws ? p.ws + b.offset + (size_t)rn.ch_off * esz : nullptr;
-    a.C = n.C; a.pitch = b.pitch; a.H = n.H; a.W = n.W; a.fp32 = b.fp32;
+    a.C = n.C; a.pitch = b.pitch; a.H = n.H; a.W = n.W; a.fp32 = b.fp32; a.f16 = p.f16;
     return a;
 }
 
@@ -176,6 +179,22 @@ int infer_shapes(RtodPlan& p) {
         if (H <= 0 || W <= 0) return fail(RTOD_ERR_BAD_ARG, "layer %d: empty output", i);
     }
     return RTOD_OK;
+}
+
+// Two-term weights (w = hi + lo in fp16, two MMAs per K step) where the extra tensor work hides behind the
+// layer's own HBM time: arithmetic intensity 2*M*N*K / bytes below roughly the machine's ridge (211 FLOP/B
+// measured), and only for layers with many output elements -- every rounded element contributes equally to the
+// prediction error of a deep network, so the large early layers dominate it ("numerics").
+// A function of the layer shape only.
+int choose_w_split(const RtodPlan& p, const Node& nd) {
+    if (!p.f16 || (p.flags & RTOD_PLAN_NO_WSPLIT) || nd.stem || nd.head) return 0;
+    const double in_px = (double)(nd.d.stride * nd.d.stride);            // input pixels read per output pixel
+    const double bytes = 2.0 * (in_px * nd.Cin + nd.d.filters * (nd.res_src >= -1 ? 2.0 : 1.0));
+    const double ai = 2.0 * nd.d.filters * nd.K / bytes;
+    double ai_max = 240.0, min_elems = 300000.0;
+    if (const char* e = getenv("RTOD_WSPLIT_AI")) ai_max = atof(e);
+    if (const char* e = getenv("RTOD_WSPLIT_ELEMS")) min_elems = atof(e);
+    return ai < ai_max && (double)nd.H * nd.W * nd.d.filters >= min_elems ? 1 : 0;
 }
 
 void add_reader(RtodPlan& p, int src, int reader) {
@@ -327,7 +346,8 @@ int build(RtodPlan& p) {
     for (int i = 0; i < n; ++i) {
         Node& nd = p.nodes[i];
         if (nd.d.type != RTOD_LAYER_CONV) continue;
-        nd.w_off = woff;  woff = align_up(woff + (size_t)nd.Cout_pad * nd.K * 2, 256);
+        nd.w_split = choose_w_split(p, nd);
+        nd.w_off = woff;  woff = align_up(woff + ((size_t)nd.Cout_pad << nd.w_split) * nd.K * 2, 256);
         nd.bias_off = woff; woff = align_up(woff + (size_t)nd.Cout_pad * 4, 256);
         if (nd.stem) { nd.wf_off = woff; woff = align_up(woff + (size_t)nd.d.filters * nd.K * 4, 256); }
         const double M = (double)p.batch * nd.H * nd.W;
@@ -402,12 +422,13 @@ int bind_layers(RtodPlan& p) {
         if (!nd.stem) a.in = act_of(p, i - 1);
         a.out = act_of(p, i);
         a.out.C = nd.d.filters;
-        a.w = reinterpret_cast<const __nv_bfloat16*>(p.wa + nd.w_off);
+        a.w = p.wa + nd.w_off;
+        a.w_split = nd.w_split;
         a.bias = reinterpret_cast<const float*>(p.wa + nd.bias_off);
         if (nd.res_src >= -1) {
             const Act r = act_of(p, nd.res_src);
             if (r.fp32) return fail(RTOD_ERR_UNSUPPORTED, "layer %d: fp32 shortcut operand", i);
-            a.res = reinterpret_cast<const __nv_bfloat16*>(r.ptr);
+            a.res = r.ptr;
             a.res_pitch = r.pitch;
         }
         a.split_scratch = reinterpret_cast<float*>(p.ws + p.split_off);
@@ -432,7 +453,7 @@ int bind_layers(RtodPlan& p) {
             if (nd.d.type != RTOD_LAYER_CONV || nd.alias_of >= -1 || !nd.use_tc) continue;
             if (prev) {
                 prev->tc.p.pf_ptr = p.wa + nd.w_off;
-                prev->tc.p.pf_bytes = (unsigned long long)nd.Cout_pad * nd.K * 2ull;     // multiple of 16
+                prev->tc.p.pf_bytes = ((unsigned long long)nd.Cout_pad << nd.w_split) * nd.K * 2ull;     // multiple of 16
             }
             prev = &nd;
         }
@@ -456,6 +477,7 @@ extern "C" int rtod_plan_create(const RtodLayerDesc* layers, int n_layers, int b
     RtodPlan* p = new (std::nothrow) RtodPlan();
     if (!p) return fail(RTOD_ERR_BAD_ARG, "rtod_plan_create: out of host memory");
     p->batch = batch; p->in_c = in_c; p->in_h = in_h; p->in_w = in_w; p->inp_dim = inp_dim; p->flags = flags;
+    p->f16 = (flags & RTOD_PLAN_BF16) ? 0 : 1;
     p->nodes.resize(n_layers);
     for (int i = 0; i < n_layers; ++i) p->nodes[i].d = layers[i];
     const int rc = build(*p);
@@ -517,7 +539,7 @@ extern "C" int rtod_plan_set_conv_weights(RtodPlan* p, int layer, const float* w
         return fail(RTOD_ERR_BAD_ARG, "rtod_plan_set_conv_weights: all four BatchNorm tensors or none");
     Node& nd = p->nodes[layer];
     const int rc = launch_fold_pack(weight, bias, bn_gamma, bn_beta, bn_mean, bn_var, bn_eps, nd.d.filters,
-                                    nd.Cin, nd.d.size, reinterpret_cast<__nv_bfloat16*>(p->wa + nd.w_off),
+                                    nd.Cin, nd.d.size, nd.Cout_pad, p->f16, nd.w_split, p->wa + nd.w_off,
                                     nd.stem ? reinterpret_cast<float*>(p->wa + nd.wf_off) : nullptr,
                                     reinterpret_cast<float*>(p->wa + nd.bias_off), (cudaStream_t)stream);
     if (rc) return rc;
@@ -671,7 +693,7 @@ extern "C" int rtod_plan_conv_backend(const RtodPlan* p, int layer) {
     const Node& nd = p->nodes[layer];
     if (nd.stem) return RTOD_CONV_STEM;
     if (!nd.use_tc) return RTOD_CONV_SIMT;
-    return nd.tc.patch == 2 ? RTOD_CONV_TC_PAIR : (nd.tc.patch == 1 ? RTOD_CONV_TC_PATCH : RTOD_CONV_TC);
+    return nd.tc.patch == 2 ? RTOD_CONV_TC_PAIR : RTOD_CONV_TC;
 }
 
 extern "C" int rtod_plan_read_layer(RtodPlan* p, int layer, float* out_nchw, void* stream) {
@@ -681,13 +703,39 @@ extern "C" int rtod_plan_read_layer(RtodPlan* p, int layer, float* out_nchw, voi
     return launch_nhwc_to_nchw(act_of(*p, layer), p->batch, out_nchw, (cudaStream_t)stream);
 }
 
+extern "C" int rtod_plan_set_error_sink(RtodPlan* p, int* host_flag, void* stream) {
+    if (!p || !p->bound) return fail(RTOD_ERR_STATE, "rtod_plan_set_error_sink: plan is not bound");
+    int* dev_view = nullptr;
+    if (host_flag) {
+        void* d = nullptr;
+        RTOD_CUDA_OK(cudaHostGetDevicePointer(&d, host_flag, 0));     // fails unless the memory is pinned and mapped
+        dev_view = static_cast<int*>(d);
+    }
+    p->err_sink = dev_view;
+    RTOD_CUDA_OK(cudaMemcpyAsync(p->err_flag + 2, &p->err_sink, sizeof(int*), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return RTOD_OK;
+}
+
+extern "C" int rtod_plan_reset_errors(RtodPlan* p, void* stream) {
+    if (!p || !p->bound) return fail(RTOD_ERR_STATE, "rtod_plan_reset_errors: plan is not bound");
+    RTOD_CUDA_OK(cudaMemsetAsync(p->err_flag, 0, sizeof(int), (cudaStream_t)stream));
+    RTOD_CUDA_OK(cudaMemsetAsync(p->ws + p->split_off + kSplitScratchBytes, 0, kSplitCounters * sizeof(int), (cudaStream_t)stream));
+    return RTOD_OK;
+}
+
+extern "C" int rtod_plan_is_f16(const RtodPlan* p) { return p ? p->f16 : 0; }
+extern "C" int rtod_plan_conv_w_split(const RtodPlan* p, int layer) {
+    if (!p || layer < 0 || layer >= (int)p->nodes.size() || p->nodes[layer].d.type != RTOD_LAYER_CONV) return 0;
+    return p->nodes[layer].w_split;
+}
+
 extern "C" int rtod_plan_check(RtodPlan* p, void* stream) {
     if (!p || !p->bound) return fail(RTOD_ERR_STATE, "rtod_plan_check: plan is not bound");
     int flag = 0;
     RTOD_CUDA_OK(cudaMemcpyAsync(&flag, p->err_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     RTOD_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
     if (flag != 0) {
-        cudaMemsetAsync(p->err_flag, 0, sizeof(int), (cudaStream_t)stream);
+        rtod_plan_reset_errors(p, stream);
         return fail(RTOD_ERR_DEVICE, "device-side failure flag %d (tcgen05/TMA pipeline time-out)", flag);
     }
     return RTOD_OK;

@@ -32,7 +32,22 @@ struct StemParams {
     int dbg;
 };
 
-template <int NT>
+template <bool kF16>
+__device__ __forceinline__ void stem_mma(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    if constexpr (kF16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// kF16: fp16 operands, weights AND image as two-term sums (three products: the stem's weight rounding would
+// otherwise be the largest single error source of the network, it touches the most output elements);
+// bf16: image hi + lo, single bf16 weights (the north-star wording's arithmetic)
+template <int NT, bool kF16>
 __global__ void __launch_bounds__(224, 4) stem_tma_kernel(const __grid_constant__ StemParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -61,7 +76,8 @@ __global__ void __launch_bounds__(224, 4) stem_tma_kernel(const __grid_constant_
         const int k = 16 * (i >> 2) + 2 * t + (i & 1) + 8 * ((i >> 1) & 1);
         koff[i] = k < 27 ? (uint32_t)((k / 3) * p.box_w + (k % 3) + 3) * 4u : 0xFFFFFFFFu;   // (c*3+ky)*box_w + kx + 3
     }
-    uint32_t bfr[NT][2][2];                              // B fragments: W[n = 8j + g][k], bf16 like every layer's weights
+    uint32_t bfr[NT][2][2];                              // B fragments: W[n = 8j + g][k]
+    uint32_t blo[kF16 ? NT : 1][2][2];                   // second term of the weights (fp16 mode)
 #pragma unroll
     for (int j = 0; j < NT; ++j)
 #pragma unroll
@@ -71,7 +87,9 @@ __global__ void __launch_bounds__(224, 4) stem_tma_kernel(const __grid_constant_
                 const int k0 = 16 * s + 2 * t + 8 * hh;
                 const float w0 = k0 < 27 ? __ldg(p.w + (8 * j + g) * 27 + k0) : 0.0f;
                 const float w1 = k0 + 1 < 27 ? __ldg(p.w + (8 * j + g) * 27 + k0 + 1) : 0.0f;
-                bfr[j][s][hh] = pack_bf16x2(w0, w1);
+                bfr[j][s][hh] = pack_h2<kF16>(w0, w1);
+                if constexpr (kF16)
+                    blo[j][s][hh] = pack_h2<kF16>(w0 - h2_lo<kF16>(bfr[j][s][hh]), w1 - h2_hi<kF16>(bfr[j][s][hh]));
             }
     float bia[NT][2];
 #pragma unroll
@@ -114,7 +132,7 @@ __global__ void __launch_bounds__(224, 4) stem_tma_kernel(const __grid_constant_
     if (threadIdx.x == 0)
         for (int l = 0; l < kStemStages - 1; ++l) issue();
 
-    __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out.ptr);
+    unsigned short* obase = reinterpret_cast<unsigned short*>(p.out.ptr);
     Pos pos = first;
     int s = 0;
     uint32_t parity = 0;
@@ -142,10 +160,10 @@ __global__ void __launch_bounds__(224, 4) stem_tma_kernel(const __grid_constant_
                     const uint32_t a1 = koff[i + 1] == 0xFFFFFFFFu ? zero_addr : stage_addr + rr * 32u + koff[i + 1];
                     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(a0));
                     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(a1));
-                    // image = hi + lo in bf16: two MMAs keep ~16 mantissa bits of the pixels
-                    const uint32_t hi = pack_bf16x2(v0, v1);
+                    // image = hi + lo: two MMAs keep ~16 (bf16) / ~22 (fp16) mantissa bits of the pixels
+                    const uint32_t hi = pack_h2<kF16>(v0, v1);
                     ahi[i >> 2][((i >> 1) & 1) * 2 + rr] = hi;
-                    alo[i >> 2][((i >> 1) & 1) * 2 + rr] = pack_bf16x2(v0 - bf16_lo(hi), v1 - bf16_hi(hi));
+                    alo[i >> 2][((i >> 1) & 1) * 2 + rr] = pack_h2<kF16>(v0 - h2_lo<kF16>(hi), v1 - h2_hi<kF16>(hi));
                 }
             float acc[NT][4];
 #pragma unroll
@@ -153,14 +171,9 @@ __global__ void __launch_bounds__(224, 4) stem_tma_kernel(const __grid_constant_
                 acc[j][0] = bia[j][0]; acc[j][1] = bia[j][1]; acc[j][2] = bia[j][0]; acc[j][3] = bia[j][1];
 #pragma unroll
                 for (int s2 = 0; s2 < 2; ++s2) {
-#define RTOD_MMA(A)                                                                                          \
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, " \
-                 "{%0,%1,%2,%3};"                                                                            \
-                 : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])                        \
-                 : "r"(A[s2][0]), "r"(A[s2][1]), "r"(A[s2][2]), "r"(A[s2][3]), "r"(bfr[j][s2][0]), "r"(bfr[j][s2][1]))
-                    RTOD_MMA(alo);
-                    RTOD_MMA(ahi);
-#undef RTOD_MMA
+                    stem_mma<kF16>(acc[j], alo[s2], bfr[j][s2]);
+                    if constexpr (kF16) stem_mma<kF16>(acc[j], ahi[s2], blo[j][s2]);
+                    stem_mma<kF16>(acc[j], ahi[s2], bfr[j][s2]);
                 }
             }
             const long long row_pix = ((long long)b * p.H + y) * p.W;
@@ -168,7 +181,7 @@ __global__ void __launch_bounds__(224, 4) stem_tma_kernel(const __grid_constant_
             for (int rr = 0; rr < 2; ++rr) {
                 const int x = x_first + px0 + g + 8 * rr;
                 if (x >= p.W) continue;
-                __nv_bfloat16* dst = obase + (row_pix + x) * p.out.pitch + 2 * t;
+                unsigned short* dst = obase + (row_pix + x) * p.out.pitch + 2 * t;
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
                     float v0 = acc[j][2 * rr], v1 = acc[j][2 * rr + 1];
@@ -176,7 +189,7 @@ __global__ void __launch_bounds__(224, 4) stem_tma_kernel(const __grid_constant_
                         v0 = fmaxf(v0, 0.1f * v0);
                         v1 = fmaxf(v1, 0.1f * v1);
                     }
-                    *reinterpret_cast<uint32_t*>(dst + 8 * j) = pack_bf16x2(v0, v1);
+                    *reinterpret_cast<uint32_t*>(dst + 8 * j) = pack_h2<kF16>(v0, v1);
                 }
             }
         }
@@ -225,9 +238,15 @@ int launch_stem_tma(const float* x, int B, int H, int W, const float* w, const f
     const int per_sm = 4;                                        // <= 72 registers/thread: four CTAs of <= 7 warps per SM
     int grid = kNumSMs * per_sm;
     if (grid > p.total_strips) grid = p.total_strips;
-    if (Cout == 32) stem_tma_kernel<4><<<grid, warps * 32, smem, stream>>>(p);
-    else if (Cout == 16) stem_tma_kernel<2><<<grid, warps * 32, smem, stream>>>(p);
-    else stem_tma_kernel<8><<<grid, warps * 32, smem, stream>>>(p);
+    if (out.f16) {
+        if (Cout == 32) stem_tma_kernel<4, true><<<grid, warps * 32, smem, stream>>>(p);
+        else if (Cout == 16) stem_tma_kernel<2, true><<<grid, warps * 32, smem, stream>>>(p);
+        else stem_tma_kernel<8, true><<<grid, warps * 32, smem, stream>>>(p);
+    } else {
+        if (Cout == 32) stem_tma_kernel<4, false><<<grid, warps * 32, smem, stream>>>(p);
+        else if (Cout == 16) stem_tma_kernel<2, false><<<grid, warps * 32, smem, stream>>>(p);
+        else stem_tma_kernel<8, false><<<grid, warps * 32, smem, stream>>>(p);
+    }
     RTOD_LAUNCH_OK("stem_tma_kernel");
     return RTOD_OK;
 }

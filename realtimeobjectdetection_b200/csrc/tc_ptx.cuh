@@ -1,5 +1,5 @@
 // tc_ptx.cuh -- inline-PTX wrappers (mbarrier, TMA, tcgen05/TMEM) and tensor-map host helpers shared by
-// the tcgen05 convolution kernels (conv_tc.cu: im2col / 1x1, conv_patch.cu: halo-patch 3x3).
+// the tcgen05 convolution kernels (conv_tc.cu: one CTA per tile, conv_pair.cu: CTA pairs).
 #pragma once
 #include <cstdlib>
 #include <cuda.h>
@@ -36,6 +36,17 @@ static __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t par
         : "memory");
     return done != 0;
 }
+// Failure block at the head of a plan's workspace: int [0] = device flag (polled by every waiting role so that
+// all of them drain), ints [2..3] = address of a host-mapped int the HOST polls without any copy or sync
+// (rtod_plan_set_error_sink); written once, on the failure path only.
+static __device__ __forceinline__ void raise_device_error(int* err_flag, int code) {
+    atomicExch(err_flag, code);
+    int* sink = *reinterpret_cast<int* volatile*>(err_flag + 2);
+    if (sink) {
+        *reinterpret_cast<volatile int*>(sink) = code;
+        __threadfence_system();
+    }
+}
 // bounded wait: false after a time-out or once another CTA has raised the failure flag.  The flag (a
 // global load, ~700 cycles) and the clock are only consulted every 64 unsuccessful polls, so a barrier
 // that flips shortly after the first poll costs no memory round trip.
@@ -48,7 +59,7 @@ static __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity,
             const unsigned long long now = global_timer_ns();
             if (t0 == 0) t0 = now;
             else if (now - t0 > kWaitTimeoutNs) {
-                atomicExch(err_flag, 2);
+                raise_device_error(err_flag, 2);
                 return false;
             }
         }
@@ -313,6 +324,15 @@ static inline int driver_fn(const char* name, void** fn) {
 
 static inline CUtensorMapSwizzle swizzle_for(int bk) {
     return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// tcgen05 kind::f16 instruction descriptor: fp32 accumulate, fp16 (format 0) or bf16 (format 1) operands, both K-major
+static inline uint32_t umma_idesc(int f16, int m, int n) {
+    const uint32_t fmt = f16 ? 0u : 1u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+static inline CUtensorMapDataType h16_tmap_type(int f16) {
+    return f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 }
 
 static inline int pick_bk(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : (cin % 16 == 0 ? 16 : 0)); }

@@ -85,12 +85,32 @@ class _Plan:
         with torch.cuda.device(device):
             _lib.check(lib.rtod_plan_bind(self.handle, ws, lib.rtod_plan_workspace_bytes(self.handle),
                                           wa, lib.rtod_plan_weight_bytes(self.handle)))
+        self.is_f16 = bool(lib.rtod_plan_is_f16(self.handle))
+        # failure reporting without a sync: kernels store a code in this pinned, device-mapped int on time-out
+        self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        with torch.cuda.device(device):
+            _lib.check(lib.rtod_plan_set_error_sink(self.handle, self.err_host.data_ptr(),
+                                                    torch.cuda.current_stream(device).cuda_stream))
         self.weight_version = None
-        self.graph = None
-        self.graph_x = None
-        self.graph_pred = None
-        self.graph_train = None
+        # CUDA graphs of the launch sequence, keyed by (input pointer, train): {"graph", "x", "pred"}.
+        # Key None = the staging graph (input copied into its own buffer first).
+        self.graphs = {}
         self.calls = 0
+        self.last_used = 0
+
+    def raise_if_failed(self):
+        """Raise (and re-arm the plan) if a kernel of an earlier forward reported a device-side failure."""
+        code = int(self.err_host[0])
+        if code == 0:
+            return
+        self.err_host[0] = 0
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            stream.synchronize()
+            _lib.check(self.lib.rtod_plan_reset_errors(self.handle, stream.cuda_stream))
+        self.graphs.clear()
+        raise _lib.RtodError(-6, "device-side failure %d in an earlier forward (tcgen05/TMA pipeline time-out); "
+                                 "its output is invalid; the plan has been re-armed" % code)
 
     def close(self):
         if self.handle:
@@ -117,10 +137,18 @@ class Darknet(nn.Module):
         self.TRAIN = False
         # -- B200 runtime state (not part of the reference surface) --
         self._plans = {}
+        self._plan_clock = 0
         self._weights_epoch = 0                    # bumped whenever parameters may have changed
-        self.plan_flags = 0                        # _lib.PLAN_KEEP_ALL / PLAN_CONV_SIMT for validation
+        # _lib.PLAN_* flags: PLAN_KEEP_ALL / PLAN_CONV_SIMT for validation, PLAN_BF16 for bf16 storage
+        # (default fp16: same tensor-core rate, 8x finer rounding), PLAN_NO_WSPLIT
+        self.plan_flags = _lib.PLAN_BF16 if os.environ.get("RTOD_DTYPE", "fp16").lower() == "bf16" else 0
         self.use_cuda_graph = os.environ.get("RTOD_CUDA_GRAPH", "1") != "0"
+        # True: forward() returns the replayed graph's own output buffer instead of a fresh copy -- valid until
+        # the next forward with the SAME input buffer (DetectionPipeline / bench: the consumer is already
+        # enqueued behind it on the stream).  False (default): reference semantics, every call a fresh tensor.
+        self.borrow_output = False
         self._warned_train_bn = False
+        self._warned_grad = False
 
     # ------------------------------------------------------------------ reference accessors
     def get_blocks(self) -> list:
@@ -318,10 +346,16 @@ class Darknet(nn.Module):
         full_key = key + (device.index, self.plan_flags)
         plan = self._plans.get(full_key)
         if plan is None:
-            if len(self._plans) >= 8:                       # bound arena memory: drop the oldest shape
-                self._plans.pop(next(iter(self._plans))).close()
-            plan = _Plan(_lib.load(), self._layer_descs(), key, device, self.plan_flags)
+            if len(self._plans) >= 8:                       # bound arena memory: drop the least recently used shape
+                victim = min(self._plans, key=lambda k: self._plans[k].last_used)
+                self._plans.pop(victim).close()
+            flags = self.plan_flags
+            if torch.cuda.is_current_stream_capturing():   # bind-time autotuning synchronises: not inside a capture
+                flags |= _lib.PLAN_NO_AUTOTUNE
+            plan = _Plan(_lib.load(), self._layer_descs(), key, device, flags)
             self._plans[full_key] = plan
+        self._plan_clock += 1
+        plan.last_used = self._plan_clock
         return plan
 
     def _sync_weights(self, plan: _Plan, stream: int):
@@ -353,7 +387,7 @@ class Darknet(nn.Module):
                 float(bn.eps) if bn is not None else 0.0, stream))
         torch.cuda.current_stream(dev).synchronize()       # staging copies in `keep` may now die
         plan.weight_version = sig
-        plan.graph = None                                   # weights live in the same arena: graph stays
+        plan.graphs.clear()                                 # weights live in the same arena: the graphs stay
         # valid, but re-capture keeps the contract simple
 
     # ------------------------------------------------------------------ forward
@@ -361,7 +395,9 @@ class Darknet(nn.Module):
         """[B, 3, H, W] fp32 -> [B, N, 5+C] fp32 (src/darknet.py:199-253); ``[]`` without yolo layers.
 
         ``CUDA`` is tolerated for callers written against the north-star wording; the reference
-        signature is ``forward(x)``.
+        signature is ``forward(x)``.  Inference only: the result carries no ``grad_fn`` (the
+        reference trainer, train.py:412-425, is out of scope -- a warning is issued once if a
+        gradient is expected).
         """
         lib = _lib.load()
         if not torch.cuda.is_available():
@@ -370,6 +406,11 @@ class Darknet(nn.Module):
             self._warned_train_bn = True
             warnings.warn("Darknet is in training mode; this implementation always evaluates "
                           "BatchNorm with running statistics (== reference .eval())", stacklevel=2)
+        if torch.is_grad_enabled() and not self._warned_grad and \
+                (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
+            self._warned_grad = True
+            warnings.warn("Darknet.forward is inference-only here: the prediction has no grad_fn, "
+                          "loss.backward() will not reach the parameters", stacklevel=2)
         if x.dim() != 4:
             raise ValueError("expected a [B, C, H, W] tensor, got %s" % (tuple(x.shape),))
         if x.is_cuda:
@@ -389,6 +430,7 @@ class Darknet(nn.Module):
 
         with torch.cuda.device(device):
             plan = self._get_plan(key, device)
+            plan.raise_if_failed()                           # a time-out reported by an earlier forward
             stream = torch.cuda.current_stream(device)
             self._sync_weights(plan, stream.cuda_stream)
             has_heads = plan.n_rows > 0
@@ -417,25 +459,38 @@ class Darknet(nn.Module):
             _lib.check(lib.rtod_plan_forward(plan.handle, x.data_ptr(), pred.data_ptr(), train,
                                              stream.cuda_stream))
             return pred
-        if plan.graph is None or plan.graph_train != train:
-            plan.graph_x = torch.empty_like(x)
-            plan.graph_pred = torch.empty(shape, dtype=torch.float32, device=plan.device)
-            graph = torch.cuda.CUDAGraph()
-            try:
-                stream.synchronize()
-                with torch.cuda.graph(graph):
-                    _lib.check(lib.rtod_plan_forward(plan.handle, plan.graph_x.data_ptr(),
-                                                     plan.graph_pred.data_ptr(), train,
-                                                     torch.cuda.current_stream(plan.device).cuda_stream))
-                plan.graph, plan.graph_train = graph, train
-            except Exception as exc:                              # capture unsupported: stay eager
-                warnings.warn("CUDA graph capture failed (%s); using stream launches" % (exc,))
-                self.use_cuda_graph = False
-                plan.graph = None
-                return self._run(plan, x, train, stream)
-        plan.graph_x.copy_(x, non_blocking=True)
-        plan.graph.replay()
-        return plan.graph_pred.clone()
+        # The launch sequence is replayed as a CUDA graph.  A graph embeds its input pointer: inputs that keep
+        # arriving in the same buffers (the pipeline's ring slots, a benchmark's resident batches) get a graph
+        # of their own -- no staging copy; any other input is copied into the staging graph's buffer.
+        entry = plan.graphs.get((x.data_ptr(), train))
+        if entry is None and self.borrow_output and len(plan.graphs) < 6:
+            entry = self._capture(plan, x, train, stream, key=(x.data_ptr(), train))
+        if entry is None:
+            entry = plan.graphs.get((None, train))
+            if entry is None:
+                entry = self._capture(plan, torch.empty_like(x), train, stream, key=(None, train))
+            if entry is not None:
+                entry["x"].copy_(x, non_blocking=True)
+        if entry is None:                                      # capture unsupported: stream launches
+            return self._run(plan, x, train, stream)
+        entry["graph"].replay()
+        return entry["pred"] if self.borrow_output else entry["pred"].clone()
+
+    def _capture(self, plan: _Plan, x: torch.Tensor, train: int, stream, key):
+        shape = (plan.key[0], plan.n_rows, plan.n_attrs)
+        entry = {"x": x, "pred": torch.empty(shape, dtype=torch.float32, device=plan.device),
+                 "graph": torch.cuda.CUDAGraph()}
+        try:
+            stream.synchronize()
+            with torch.cuda.graph(entry["graph"]):
+                _lib.check(plan.lib.rtod_plan_forward(plan.handle, x.data_ptr(), entry["pred"].data_ptr(), train,
+                                                      torch.cuda.current_stream(plan.device).cuda_stream))
+        except Exception as exc:                              # capture unsupported: stay eager
+            warnings.warn("CUDA graph capture failed (%s); using stream launches" % (exc,))
+            self.use_cuda_graph = False
+            return None
+        plan.graphs[key] = entry
+        return entry
 
     # ------------------------------------------------------------------ validation helpers
     def read_layer(self, index: int, key=None) -> torch.Tensor:

@@ -5,17 +5,22 @@ reference's loop is detect.py:57-80 -- synchronous pageable ``.cuda()`` per imag
     pipe = DetectionPipeline(model, num_class=80, confidence=0.5, nms_conf=0.4)
     for det in pipe.run(host_batches):        # det: [D, 8] tensor on the host, or int 0
         ...
+
+``host_batches`` yields either ``[B, 3, H, W]`` fp32 tensors (what ``prep_image`` returns) or **uint8
+``[B, h, w, 3]`` BGR frames** as a camera / ``cv2.imread`` delivers them: those are copied as bytes (a
+quarter of the fp32 traffic at network resolution) and letterboxed, channel-swapped and scaled by one kernel
+on the device (``util.prep_frames``, src/util.py:349-397).
 """
 from __future__ import annotations
 
 import torch
 
-from .util import write_results_async
+from .util import prep_frames, write_results_async
 
 
 class DetectionPipeline:
     def __init__(self, model, num_class: int, confidence: float = 0.6, nms_conf: float = 0.4,
-                 device=None, depth: int = 2, collect_lag: int = 1):
+                 device=None, depth: int = 2, collect_lag: int = 1, resize: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("DetectionPipeline needs a CUDA device; there is no CPU fallback")
         self.model, self.num_class = model, int(num_class)
@@ -26,6 +31,7 @@ class DetectionPipeline:
         # idles on the host.  0 (live video, per-frame latency): every batch is collected before the next frame
         # is requested from the source.
         self.collect_lag = 1 if collect_lag else 0
+        self.resize = int(resize)                              # util.RESIZE_FLOAT / RESIZE_OPENCV for uint8 frames
         self.copy_stream = torch.cuda.Stream(self.device)
         self._slots = []
         self.h2d_bytes = 0
@@ -33,15 +39,18 @@ class DetectionPipeline:
 
     def _slot(self, k, like):
         while len(self._slots) <= k:
-            self._slots.append({"buf": None, "ready": torch.cuda.Event(), "free": torch.cuda.Event()})
+            self._slots.append({"buf": None, "x": None, "ready": torch.cuda.Event(), "free": torch.cuda.Event()})
         s = self._slots[k]
-        if s["buf"] is None or s["buf"].shape != like.shape:
-            s["buf"] = torch.empty(like.shape, dtype=torch.float32, device=self.device)
+        if s["buf"] is None or s["buf"].shape != like.shape or s["buf"].dtype != like.dtype:
+            s["buf"] = torch.empty(like.shape, dtype=like.dtype, device=self.device)
+            s["x"] = None                                      # fp32 network input of uint8 slots, made on demand
             s["free"].record(torch.cuda.current_stream(self.device))
         return s
 
     def _stage(self, k, host):
         """enqueue the H2D copy of one host batch into ring slot k on the copy stream"""
+        if host.dtype not in (torch.float32, torch.uint8):
+            raise TypeError("DetectionPipeline takes fp32 [B,3,H,W] or uint8 [B,h,w,3] batches, got %s" % (host.dtype,))
         s = self._slot(k % self.depth, host)
         if not host.is_pinned():
             host = host.pin_memory()
@@ -52,9 +61,19 @@ class DetectionPipeline:
         self.h2d_bytes += host.numel() * host.element_size()
         return s
 
+    def _network_input(self, slot):
+        """the slot's frames as the fp32 [B, 3, D, D] tensor the network reads (a stable buffer per slot, so the
+        forward replays one CUDA graph per slot)"""
+        if slot["buf"].dtype == torch.float32:
+            return slot["buf"]
+        dim = int(self.model.net_info["height"])
+        if slot["x"] is None or slot["x"].size(2) != dim:
+            slot["x"] = torch.empty(slot["buf"].size(0), 3, dim, dim, dtype=torch.float32, device=self.device)
+        return prep_frames(slot["buf"], dim, "BGR", self.resize, out=slot["x"])
+
     def run(self, host_batches):
-        """host_batches: iterable of [B, 3, H, W] fp32 host tensors (pinned memory avoids a staging
-        copy).  Yields write_results() of every batch, on the host."""
+        """host_batches: iterable of host tensors (pinned memory avoids a staging copy).  Yields
+        write_results() of every batch, on the host."""
         it = iter(host_batches)
         compute = torch.cuda.current_stream(self.device)
         try:
@@ -63,26 +82,31 @@ class DetectionPipeline:
             return
         k = 0
         prev = None                                            # detections of the previous batch, not yet collected
-        while pending is not None:
-            nxt = None
-            try:
-                nxt = self._stage(k + 1, next(it))            # overlaps this batch's compute
-            except StopIteration:
-                pass
-            compute.wait_event(pending["ready"])
-            pred = self.model(pending["buf"])
-            handle = write_results_async(pred, self.num_class, self.confidence, self.nms_conf)
-            pending["free"].record(compute)
-            if self.collect_lag == 0:
-                yield self._collect(handle)
-            else:
-                # this batch is in the stream: only now wait for the previous one (the GPU keeps working)
-                if prev is not None:
-                    yield self._collect(prev)
-                prev = handle
-            pending, k = nxt, k + 1
-        if prev is not None:
-            yield self._collect(prev)
+        borrow = getattr(self.model, "borrow_output", False)
+        self.model.borrow_output = True                        # predictions are consumed in-stream: no copies around the graph
+        try:
+            while pending is not None:
+                nxt = None
+                try:
+                    nxt = self._stage(k + 1, next(it))        # overlaps this batch's compute
+                except StopIteration:
+                    pass
+                compute.wait_event(pending["ready"])
+                pred = self.model(self._network_input(pending))
+                handle = write_results_async(pred, self.num_class, self.confidence, self.nms_conf)
+                pending["free"].record(compute)
+                if self.collect_lag == 0:
+                    yield self._collect(handle)
+                else:
+                    # this batch is in the stream: only now wait for the previous one (the GPU keeps working)
+                    if prev is not None:
+                        yield self._collect(prev)
+                    prev = handle
+                pending, k = nxt, k + 1
+            if prev is not None:
+                yield self._collect(prev)
+        finally:
+            self.model.borrow_output = borrow
 
     def _collect(self, handle):
         det = handle.result(to_host=True)

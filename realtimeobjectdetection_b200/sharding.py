@@ -25,7 +25,9 @@ def gather_detections(local_rows, first_frame: int, group=None, dst: int = 0):
 
     Returns, on ``dst``, the concatenated ``[D, 8]`` tensor (image index made global) or 0 when no
     rank has a detection; on other ranks returns None.  Two collectives: an all_gather of the
-    counts (one int64 per rank) and a padded gather of the rows.
+    counts (one int64 per rank) and a padded gather of the rows -- exact for any size, but the counts
+    are read on the host; a streaming loop uses ``gather_detections_async`` (one fixed-capacity
+    collective, no host synchronisation) instead.
     """
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
@@ -51,6 +53,81 @@ def gather_detections(local_rows, first_frame: int, group=None, dst: int = 0):
         return torch.cat([b[:c] for b, c in zip(bucket, counts)], 0)
     dist.gather(padded, None, dst=dst, group=group)
     return None
+
+
+class PendingGather:
+    """Handle of an enqueued fixed-capacity gather (``gather_detections_async``)."""
+
+    def __init__(self, rank, dst, world, capacity, bucket_host, done, work):
+        self._rank, self._dst, self._world, self._cap = rank, dst, world, capacity
+        self._bucket_host, self._done, self._work = bucket_host, done, work
+
+    def result(self):
+        """On ``dst``: the concatenated ``[D, 8]`` rows (image index global) or 0; elsewhere None.  Waits only for
+        the event recorded behind this gather's own copy -- later work on the compute stream keeps running."""
+        if self._work is not None:                           # CPU (gloo) path
+            self._work.wait()
+        if self._rank != self._dst:
+            return None
+        if self._done is not None:
+            self._done.synchronize()
+        parts = []
+        for r in range(self._world):
+            n = int(self._bucket_host[r, 0, 0])
+            if n > self._cap:
+                raise RuntimeError("rank %d produced %d detections, gather capacity is %d rows per rank: "
+                                   "raise `capacity`" % (r, n, self._cap))
+            if n:
+                parts.append(self._bucket_host[r, 1:1 + n])
+        return torch.cat(parts, 0).clone() if parts else 0
+
+
+_GATHER_STREAMS = {}
+
+
+def gather_detections_async(rows, count, first_frame: int, capacity: int, group=None, dst: int = 0) -> PendingGather:
+    """One fixed-capacity collective per step, no host synchronisation on the way in.
+
+    ``rows``: this rank's ``[>= D_r, 8]`` detection buffer (``PendingDetections.rows_device``: only the first
+    ``count`` rows are meaningful), ``count``: int32 tensor holding ``D_r`` (device-resident: it is never read
+    on the host here).  Every rank contributes ``capacity + 1`` rows: row 0 carries the count in-band, rows
+    1.. the detections with the image column shifted by ``first_frame``.  With NCCL the gather and the copy of
+    the bucket to pinned host memory run on a side stream behind an event, so the compute stream goes straight on
+    to the next batch; ``.result()`` is meant to be called one step late."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    nccl = dist.get_backend(group) == "nccl"
+    dev = rows.device if nccl else torch.device("cpu")
+    payload = torch.zeros(capacity + 1, 8, dtype=torch.float32, device=dev)
+    n_rows = min(capacity, rows.size(0))
+    cnt = count.to(dev).reshape(-1)[:1]
+    payload[1:1 + n_rows] = rows[:n_rows].to(dev)
+    payload[1:, 0] += float(first_frame)
+    valid = torch.arange(capacity, device=dev).unsqueeze(1) < cnt         # rows beyond the count: stale buffer content
+    payload[1:] *= valid
+    payload[0, 0] = cnt.to(torch.float32)[0]                               # exact up to 2^24 rows
+    bucket = torch.empty(world, capacity + 1, 8, dtype=torch.float32, device=dev) if rank == dst else None
+    if not nccl:
+        work = dist.gather(payload, list(bucket.unbind(0)) if rank == dst else None, dst=dst, group=group, async_op=True)
+        return PendingGather(rank, dst, world, capacity, bucket, None, work)
+    key = dev.index
+    if key not in _GATHER_STREAMS:
+        _GATHER_STREAMS[key] = torch.cuda.Stream(dev)
+    side = _GATHER_STREAMS[key]
+    ready = torch.cuda.Event()
+    ready.record(torch.cuda.current_stream(dev))
+    done, host = None, None
+    with torch.cuda.stream(side):
+        side.wait_event(ready)
+        dist.gather(payload, list(bucket.unbind(0)) if rank == dst else None, dst=dst, group=group)
+        payload.record_stream(side)
+        if rank == dst:
+            bucket.record_stream(side)
+            host = torch.empty(bucket.shape, dtype=torch.float32, pin_memory=True)
+            host.copy_(bucket, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(side)
+    return PendingGather(rank, dst, world, capacity, host, done, None)
 
 
 def detect_sharded(model, frames: torch.Tensor, num_class: int, confidence: float, nms_conf: float,

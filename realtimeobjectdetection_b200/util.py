@@ -124,6 +124,8 @@ class PendingDetections:
         self._rows, self._count_host, self._event = rows, count_host, event
         self._home, self._cap, self._device = home, cap, device
         self._d = None
+        self.rows_device = rows              # [cap, 8]: the first count_device[0] rows are the detections
+        self.count_device = None             # int32 [1] on the device (set by write_results_async)
 
     def result(self, to_host: bool = False):
         """``[D, 8]`` rows or the int ``0`` (the reference's convention).  Waits only for the event recorded
@@ -189,6 +191,7 @@ def write_results_async(prediction, num_class, confidence=0.6, nms_conf=0.4) -> 
     event.record(torch.cuda.current_stream(dev))
     pending = PendingDetections(rows, count_host, event, home, cap, dev)
     pending._keep = (x, count)                                 # alive until the kernels have run
+    pending.count_device = count
     return pending
 
 
@@ -201,3 +204,120 @@ def write_results(prediction, num_class, confidence=0.6, nms_conf=0.4):
     by row index (the reference's ``torch.sort`` leaves that order unspecified).
     """
     return write_results_async(prediction, num_class, confidence, nms_conf).result()
+
+
+# ---------------------------------------------------------------------------------------------------
+# callers either side of the hot path (SURVEY.md section 8(f)): pre-processing, box rescale, IoU matrix
+# ---------------------------------------------------------------------------------------------------
+RESIZE_FLOAT, RESIZE_OPENCV = 0, 1
+
+
+def letterbox_geometry(img_w: int, img_h: int, inp_dim: int):
+    """``(new_w, new_h, left, top)`` of ``letterbox_image`` (src/util.py:360-369) on a square canvas."""
+    lib = _lib.load()
+    out = [ctypes.c_int() for _ in range(4)]
+    _lib.check(lib.rtod_letterbox_geometry(int(img_w), int(img_h), int(inp_dim), *[ctypes.byref(v) for v in out]))
+    return tuple(v.value for v in out)
+
+
+def _as_u8_frames(img):
+    """uint8 ``[B, H, W, 3]`` tensor view of a numpy / torch HWC image or batch, and whether a batch axis was added."""
+    t = torch.from_numpy(img) if not isinstance(img, torch.Tensor) else img
+    if t.dtype != torch.uint8:
+        raise TypeError("expected uint8 HWC frames (what cv2.imread returns), got %s" % (t.dtype,))
+    single = t.dim() == 3
+    if single:
+        t = t.unsqueeze(0)
+    if t.dim() != 4 or t.size(3) != 3:
+        raise ValueError("expected [H, W, 3] or [B, H, W, 3], got %s" % (tuple(t.shape),))
+    return t, single
+
+
+def prep_frames(frames, inp_dim: int, mode: str = "BGR", resize: int = RESIZE_FLOAT, out: torch.Tensor = None,
+                as_uint8: bool = False) -> torch.Tensor:
+    """Batched, device-resident ``prep_image``: uint8 ``[B, H, W, 3]`` frames (host or device) ->
+    ``[B, 3, inp_dim, inp_dim]`` fp32 (or uint8 planes) ON THE GPU, one kernel (src/util.py:349-397)."""
+    assert mode in ("BGR", "RGB")
+    lib = _lib.load()
+    t, _ = _as_u8_frames(frames)
+    if t.is_cuda:
+        dev = t.device
+    else:
+        _require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = t.to(dev, non_blocking=True)
+    t = t.contiguous()
+    B, H, W = t.size(0), t.size(1), t.size(2)
+    dtype = torch.uint8 if as_uint8 else torch.float32
+    if out is None:
+        out = torch.empty(B, 3, int(inp_dim), int(inp_dim), dtype=dtype, device=dev)
+    elif out.shape != (B, 3, int(inp_dim), int(inp_dim)) or out.dtype != dtype or not out.is_contiguous():
+        raise ValueError("prep_frames: `out` must be a contiguous %s [%d, 3, %d, %d] tensor" % (dtype, B, inp_dim, inp_dim))
+    with torch.cuda.device(dev):
+        _lib.check(lib.rtod_prep_image(t.data_ptr(), B, H, W, int(inp_dim), int(mode == "RGB"), int(resize),
+                                       int(as_uint8), out.data_ptr(), _stream_ptr(dev)))
+    out._rtod_keep = t                                            # the staged frames live until the kernel ran
+    return out
+
+
+def prep_image(img, inp_dim, mode="BGR", resize: int = RESIZE_FLOAT) -> torch.Tensor:
+    """``prep_image(img, inp_dim, mode='BGR')`` -- src/util.py:375-397: letterbox (cubic resize, 128 fill),
+    BGR->RGB, HWC->CHW, ``/255``; returns ``[1, 3, inp_dim, inp_dim]`` fp32 on the device the image came from
+    (the host for a numpy image, like the reference)."""
+    t, single = _as_u8_frames(img)
+    if not single:
+        raise ValueError("prep_image takes one [H, W, 3] image; use prep_frames for a batch")
+    out = prep_frames(t, inp_dim, mode, resize)
+    return out if t.is_cuda else out.cpu()
+
+
+def letterbox_image(img, inp_dim, resize: int = RESIZE_FLOAT):
+    """``letterbox_image(img, (w, h))`` -- src/util.py:349-372 for square canvases; returns the ``[h, w, 3]``
+    canvas (channel order untouched) as an int64 numpy array like the reference."""
+    w, h = inp_dim
+    if w != h:
+        raise ValueError("only square canvases are supported (the reference always passes (inp_dim, inp_dim))")
+    t, single = _as_u8_frames(img)
+    planes = prep_frames(t, w, "RGB", resize, as_uint8=True)            # "RGB" = keep the channel order
+    canvas = planes[0].permute(1, 2, 0).contiguous().cpu().numpy().astype("int64")
+    return canvas
+
+
+def rescale_boxes(output: torch.Tensor, im_dim_list: torch.Tensor, inp_dim: int, ref_dim: int = 416):
+    """detect.py:120-136 on the device: map the boxes of ``write_results`` rows from letterbox to source-image
+    pixels (scale ``min(ref_dim / w, ref_dim / h)``: the reference hard-codes 416 at detect.py:130 -- pass
+    ``ref_dim=inp_dim`` for other resolutions) and clamp them to the image.  ``im_dim_list``: ``[n_img, 4]``
+    rows ``(w, h, w, h)``.  Returns ``(rows, im_dim_rows)``; inputs are not modified."""
+    lib = _lib.load()
+    x, dev, home = _to_device(output)
+    dims = im_dim_list.detach().to(device=dev, dtype=torch.float32).contiguous()
+    if x.dim() != 2 or x.size(1) != 8 or dims.dim() != 2 or dims.size(1) != 4:
+        raise ValueError("rescale_boxes expects [D, 8] rows and [n_img, 4] sizes")
+    out = torch.empty_like(x)
+    out_dims = torch.empty(x.size(0), 4, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.rtod_rescale_boxes(x.data_ptr(), x.size(0), dims.data_ptr(), dims.size(0), int(inp_dim),
+                                          int(ref_dim), out.data_ptr(), out_dims.data_ptr(), _stream_ptr(dev)))
+    return out.to(home), out_dims.to(home)
+
+
+def metrics_rows(prediction):
+    """What the reference stores in ``metrics.json`` per image name (detect.py:107, 155, 164): the
+    ``write_results`` rows as nested lists, or the int 0."""
+    return prediction if isinstance(prediction, int) else prediction.detach().cpu().tolist()
+
+
+def bbox_iou_matrix(pred: torch.Tensor, target: torch.Tensor, threshold=None) -> torch.Tensor:
+    """test.py:139-151 as one kernel: ``[P, T]`` matrix of ``bbox_iou(pred[i, 1:5], target[j, 0:4])``;
+    with ``threshold`` the entries that are not ``> threshold`` are zeroed like the validator does."""
+    lib = _lib.load()
+    p, dev, home = _to_device(pred)
+    t = target.detach().to(device=dev, dtype=torch.float32).contiguous()
+    if p.dim() != 2 or t.dim() != 2 or p.size(1) < 5 or t.size(1) < 4:
+        raise ValueError("bbox_iou_matrix expects pred [P, >=5] (boxes in columns 1:5) and target [T, >=4]")
+    out = torch.empty(p.size(0), t.size(0), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.rtod_bbox_iou_matrix(p.data_ptr() + 4, p.size(0), p.size(1), t.data_ptr(), t.size(0), t.size(1),
+                                            int(threshold is not None), float(threshold or 0.0), out.data_ptr(),
+                                            _stream_ptr(dev)))
+    return out.to(home)

@@ -234,11 +234,106 @@ def golden_forward():
         os.remove(wpath)
 
 
+# ---------------------------------------------------------------- pre-processing ---------
+def golden_prep():
+    """util.prep_image / letterbox_image (src/util.py:349-397) on the reference's own images.  cv2 is a
+    third-party dependency (this container: the stock wheel, which routes 8-bit cubic resizes to IPP):
+    the oracle's "opencv" mode must equal the reference bit for bit with IPP switched off, its "float" mode
+    must stay within one grey level of the IPP result on a vanishing fraction of the values."""
+    import glob
+    import cv2
+    from oracle import prep_port
+    worst_frac = 0.0
+    for path in sorted(glob.glob("/root/reference/imgs/*.jpg")):
+        img = cv2.imread(path)
+        for dim in (416, 608, 320):
+            cv2.ipp.setUseIPP(False)
+            want = ref_util.prep_image(img, dim)
+            assert torch.equal(want, prep_port.prep_image(img, dim, resize="opencv")), (path, dim)
+            assert np.array_equal(ref_util.letterbox_image(img, (dim, dim)),
+                                  prep_port.letterbox_image(img, (dim, dim), "opencv")), (path, dim)
+            cv2.ipp.setUseIPP(True)
+            ipp = ref_util.prep_image(img, dim)
+            mine = prep_port.prep_image(img, dim, resize="float")
+            diff = (ipp - mine).abs() * 255.0
+            assert float(diff.max()) <= 1.0001, (path, dim)
+            worst_frac = max(worst_frac, float((diff > 0.5).float().mean()))
+    assert worst_frac < 5e-4, worst_frac
+    print("   prep: oracle == reference (IPP off) on 11 images x 3 sizes; float mode vs IPP: one grey level on "
+          "<= %.4f %% of the values" % (100 * worst_frac))
+    # committed fixtures: two of the reference's images (one portrait, one landscape), their canvases from
+    # cv2 with IPP off (the oracle's exact target) and where the IPP-backed result differs from it
+    for name, dim in (("img1", 416), ("img4", 320)):
+        img = cv2.imread("/root/reference/imgs/%s.jpg" % name)
+        cv2.ipp.setUseIPP(False)
+        canvas = ref_util.letterbox_image(img, (dim, dim)).astype(np.uint8)
+        rgb = ref_util.prep_image(img, dim)
+        assert torch.equal(rgb, torch.from_numpy(canvas[:, :, ::-1].transpose(2, 0, 1).copy()).float().div(255.0).unsqueeze(0))
+        cv2.ipp.setUseIPP(True)
+        canvas_ipp = ref_util.letterbox_image(img, (dim, dim)).astype(np.uint8)
+        where = np.flatnonzero(canvas_ipp != canvas).astype(np.int32)
+        save("prep_%s_%d" % (name, dim), img=img, inp_dim=np.int64(dim), canvas=canvas,
+             ipp_index=where, ipp_value=canvas_ipp.reshape(-1)[where])
+
+
+# ---------------------------------------------------------------- post-processing --------
+def golden_post():
+    """detect.py:120-136 (box rescale + clamp) by calling the reference's own methods, and test.py:139-151
+    (validator IoU matrix; test.py itself needs matplotlib and cannot be imported: the loop is replayed here
+    around the reference's bbox_iou)."""
+    import detect as ref_detect
+    from oracle import post_port
+    rng = np.random.RandomState(5)
+
+    class Stub:
+        pass
+
+    for name, inp_dim, n_img, D in (("416", 416, 5, 40), ("608", 608, 3, 25), ("320", 320, 1, 7)):
+        dims = np.stack([rng.randint(200, 1400, n_img), rng.randint(150, 1100, n_img)], 1).astype(np.float32)
+        im_dim_list = torch.from_numpy(dims).repeat(1, 2)                       # detect.py:247-248
+        rows = np.zeros((D, 8), np.float32)
+        rows[:, 0] = np.sort(rng.randint(0, n_img, D))
+        c = rng.uniform(-20, inp_dim + 20, (D, 2)); wh = np.exp(rng.uniform(2, 5.5, (D, 2)))
+        rows[:, 1:3], rows[:, 3:5] = c - wh / 2, c + wh / 2
+        rows[:, 5:7] = rng.uniform(0.5, 1, (D, 2)); rows[:, 7] = rng.randint(0, 80, D)
+        out = torch.from_numpy(rows.copy())
+        stub = Stub()
+        stub.inp_dim = inp_dim
+        sel = ref_detect.Darknetv3Detector.convert_box_dims_to_original_image(stub, 0, im_dim_list.clone(), out)
+        ref_detect.Darknetv3Detector.clamp_box_dims(stub, sel, out)
+        got, got_dims = post_port.rescale_boxes(torch.from_numpy(rows), im_dim_list, inp_dim)
+        assert torch.equal(got, out) and torch.equal(got_dims, sel), name
+        save("rescale_" + name, rows=rows, im_dim_list=im_dim_list.numpy(), inp_dim=np.int64(inp_dim), out=out.numpy(),
+             dims=sel.numpy())
+
+    for name, P, T, thr in (("p12_t7", 12, 7, 0.5), ("p40_t1", 40, 1, 0.4), ("p3_t50", 3, 50, 0.0)):
+        def boxes(n):
+            c = rng.uniform(0, 416, (n, 2)); wh = np.exp(rng.uniform(3, 5, (n, 2)))
+            return np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+        tb = boxes(T)
+        pb = boxes(P)
+        pb[: min(P, T)] = tb[: min(P, T)] + rng.randn(min(P, T), 4).astype(np.float32) * 6     # overlapping pairs
+        pred = np.concatenate([np.zeros((P, 1), np.float32), pb, rng.uniform(0, 1, (P, 3)).astype(np.float32)], 1)
+        target = np.concatenate([tb, np.ones((T, 1), np.float32)], 1)
+        ious = []
+        for box in torch.from_numpy(pred):                                      # test.py:141-149
+            row = []
+            for t_box in torch.from_numpy(target):
+                iou = ref_util.bbox_iou(box[1:5].cpu(), t_box[0:4].cpu())
+                row.append(iou.item() if iou.item() > thr else 0.0)
+            ious.append(row)
+        want = torch.FloatTensor(ious)
+        assert torch.equal(want, post_port.iou_matrix(torch.from_numpy(pred), torch.from_numpy(target), thr)), name
+        save("ioumat_" + name, pred=pred, target=target, threshold=np.float64(thr), out=want.numpy())
+
+
 if __name__ == "__main__":
     golden_cfg()
     golden_decode()
     golden_nms()
     golden_forward()
+    golden_prep()
+    golden_post()
     with open(os.path.join(HERE, "MANIFEST.json"), "w") as fh:
         json.dump(SUMMARY, fh, indent=1, sort_keys=True)
     print("oracle == reference on every case; fixtures written to", HERE)

@@ -14,17 +14,17 @@ from conftest import ROOT
 from helpers import make_network
 from realtimeobjectdetection_b200 import Darknet, _lib, builtin_cfg, synth
 from realtimeobjectdetection_b200.cfg import parse_cfg
-from realtimeobjectdetection_b200.sharding import gather_detections, shard_bounds
+from realtimeobjectdetection_b200.sharding import gather_detections, gather_detections_async, shard_bounds
 
 
 def test_library_exports_every_declared_symbol(lib):
     header = open(os.path.join(ROOT, "include", "rtod.h")).read()
-    declared = sorted(set(re.findall(r"\b(rtod_[a-z_]+)\s*\(", header)))
+    declared = sorted(set(re.findall(r"\b(rtod_[a-z0-9_]+)\s*\(", header)))
     assert len(declared) >= 20
     for name in declared:
         assert getattr(lib, name) is not None, name
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared
-    assert lib.rtod_abi_version() == 1
+    assert lib.rtod_abi_version() == 2
 
 
 def _create(lib, model, batch, hw, inp_dim, flags=0, in_c=3):
@@ -127,6 +127,14 @@ def test_shard_bounds_cover_batch():
             assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
 
 
+def rows_match(a, b):
+    if a is None or b is None:
+        return a is None and b is None
+    if isinstance(a, int) or isinstance(b, int):
+        return isinstance(a, int) and isinstance(b, int) and a == b
+    return torch.equal(a, b)
+
+
 def _gather_worker(rank, world, port, case, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -141,6 +149,22 @@ def _gather_worker(rank, world, port, case, ret):
         else:
             local = 0
         out = gather_detections(local, first_frame=rank * 4)
+        # the streaming variant: fixed capacity, count in-band, unsliced row buffer + device-style count tensor
+        buf = torch.full((6, 8), 7.0)                          # stale content beyond the count must not leak
+        n = 0 if isinstance(local, int) else local.size(0)
+        if n:
+            buf[:n] = local
+        out2 = gather_detections_async(buf, torch.tensor([n], dtype=torch.int32), rank * 4, capacity=5).result()
+        assert rows_match(out, out2)
+        if rank == 0:
+            try:
+                gather_detections_async(buf, torch.tensor([n + 6], dtype=torch.int32), 0, capacity=5).result()
+                overflow = False
+            except RuntimeError:
+                overflow = True
+            assert overflow
+        else:
+            gather_detections_async(buf, torch.tensor([n + 6], dtype=torch.int32), 0, capacity=5).result()
         if rank == 0:
             ret.put(out if isinstance(out, int) else out.clone())
         else:
