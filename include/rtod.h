@@ -137,6 +137,11 @@ enum {
 };
 int rtod_plan_conv_backend(const RtodPlan* plan, int layer);
 
+/* launch configuration of convolution `layer` of a bound plan (tests, profiling): out12 = {backend, N tile, CTAs per
+ * SM, resident weights, staging slices, split-K, epilogue warps, activation producers, pipelines per CTA, ring
+ * stages, two-term weights, grid size} */
+int rtod_plan_conv_config(const RtodPlan* plan, int layer, int* out12);
+
 /* Debug/validation: copy one layer's output to fp32 NCHW [batch, c, h, w].  Meaningful after a
  * forward of a plan created with RTOD_PLAN_KEEP_ALL (or for the last layer). */
 int rtod_plan_read_layer(RtodPlan* plan, int layer, float* out_nchw, void* stream);

@@ -12,7 +12,7 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtod.so")
+LIB_PATH = os.environ.get("RTOD_LIB") or os.path.join(_HERE, "librtod.so")    # RTOD_LIB: bring-up builds (make TRACE=1)
 CSRC_DIR = os.path.join(_HERE, "csrc")
 ABI_VERSION = 2
 
@@ -65,6 +65,7 @@ _PROTOTYPES = {
     "rtod_plan_forward_segments": (_i, [_vp, _vp, _vp, _i, _vp, ctypes.POINTER(_f), ctypes.POINTER(_f)]),
     "rtod_plan_layer_flops": (ctypes.c_double, [_vp, _i]),
     "rtod_plan_conv_backend": (_i, [_vp, _i]),
+    "rtod_plan_conv_config": (_i, [_vp, _i, ctypes.POINTER(_i)]),
     "rtod_plan_read_layer": (_i, [_vp, _i, _vp, _vp]),
     "rtod_plan_check": (_i, [_vp, _vp]),
     "rtod_plan_set_error_sink": (_i, [_vp, _vp, _vp]),

@@ -16,6 +16,15 @@ namespace rtod {
 
 constexpr uint32_t kEpiSlice = 4096;            // one warp's staging slice: 32 rows x 128 B
 
+// TMEM column of output channel n (relative to the tile) inside an accumulator buffer.  Plain tiles: n.
+// Concatenated two-term weights on a CTA pair (each CTA supplies BN/2 hi rows followed by BN/2 lo rows of B):
+// the accumulator holds [hi 0..BN/2 | lo 0..BN/2 | hi BN/2..BN | lo BN/2..BN].
+static __device__ __forceinline__ uint32_t acc_column(const ConvTcParams& p, int n) {
+    if (!p.w_cat || p.lo_col == p.BN) return (uint32_t)n;
+    const int half = p.BN >> 1;
+    return (uint32_t)(n < half ? n : n + half);
+}
+
 // ew: epilogue warp index (0 .. kEpiWarps-1; warps ew and ew+4 share a lane quarter)
 // origin(tile, m0, n0): first row / first channel of the tile in the output matrix
 // release(buf): arrive on the accumulator-empty barrier the MMA issuer waits on (called by one lane)
@@ -58,7 +67,7 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
             if (elect_one()) release(buf);
             continue;
         }
-        const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.BN) + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.acc_cols) + ((uint32_t)(quarter * 32) << 16);
         for (int c = cg; c < n_chunks; c += kColGroups, ++g) {
             const uint32_t sb = sbufs == 2 ? (g & 1u) : 0u;
             uint8_t* slice = my_stage + sb * kEpiSlice;
@@ -71,8 +80,11 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
             }
             for (int h = 0; h < halves; ++h) {
                 uint32_t v[32];
-                if (!(p.dbg & 32)) tmem_ld_32x32(tmem_acc + (uint32_t)(c * ecols + h * 32), v);
-                else {
+                if (!(p.dbg & 32)) {
+                    const uint32_t col = acc_column(p, c * ecols + h * 32);
+                    tmem_ld_32x32(tmem_acc + col, v);
+                    if (p.w_cat) tmem_ld_add_32x32(tmem_acc + col + (uint32_t)p.lo_col, v);      // hi + lo term
+                } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = (uint32_t)(j + lane);
                 }
@@ -183,12 +195,14 @@ static __device__ __forceinline__ void conv_epilogue_split(const ConvTcParams& p
         tc_fence_after();
         // ---- pass 1: raw accumulator -> scratch ----------------------------------------------------------
         if (cg < n_chunks) {
-            const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.BN) + ((uint32_t)(quarter * 32) << 16);
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.acc_cols) + ((uint32_t)(quarter * 32) << 16);
             float* part = p.split_scratch + ((size_t)(tile * S + slice_k) * kBM + row) * p.BN;
             for (int c = cg; c < n_chunks; c += kColGroups)
                 for (int h = 0; h < halves; ++h) {
                     uint32_t v[32];
-                    tmem_ld_32x32(tmem_acc + (uint32_t)(c * ecols + h * 32), v);
+                    const uint32_t col = acc_column(p, c * ecols + h * 32);
+                    tmem_ld_32x32(tmem_acc + col, v);
+                    if (p.w_cat) tmem_ld_add_32x32(tmem_acc + col + (uint32_t)p.lo_col, v);
                     float4* dst = reinterpret_cast<float4*>(part + c * ecols + h * 32);
 #pragma unroll
                     for (int q = 0; q < 8; ++q)

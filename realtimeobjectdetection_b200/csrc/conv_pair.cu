@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
     const uint32_t rank = cluster_ctarank();             // 0 = leader (issues the MMAs), 1 = peer
     const int tile_first = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
     const uint32_t row_bytes = (uint32_t)p.BK * 2u;
-    const uint32_t a_bytes = kBM * row_bytes, b_bytes = (uint32_t)(p.BN / 2) * row_bytes;   // half of B per CTA
+    // half of the weight tile per CTA; two-term weights: the hi half-tile, then the lo half-tile
+    const uint32_t a_bytes = kBM * row_bytes, b_half = (uint32_t)(p.BN / 2) * row_bytes, b_bytes = b_half << p.w_split;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     uint8_t* epi_stage = smem + (size_t)p.stages * stage_bytes;          // [kEpilogueWarps][stage_bufs][kEpiSlice]
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + (size_t)kEpilogueWarps * p.stage_bufs * kEpiSlice);
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
                         if (p.ks > 1) tma_load_im2col_4d_pair(a_dst, &p.tmA, lead_full, c0, ow, oh, on, off_w, off_h);
                         else tma_load_2d_pair(a_dst, &p.tmA, lead_full, c0, m0);
                         tma_load_2d_pair(a_dst + a_bytes, &p.tmB, lead_full, k0, nrow0);
+                        if (p.w_split) tma_load_2d_pair(a_dst + a_bytes + b_half, &p.tmB, lead_full, k0, p.cout_pad + nrow0);
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1u;
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
                 if (!mbar_wait(&acc_empty[buf], ((uint32_t)(local >> 1) & 1u) ^ 1u, p.err_flag)) break;
                 TRACE_ADD(dbg_wacc, w0);
                 tc_fence_after();
-                const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.BN);
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.acc_cols);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     TRACE_T0(w1);
                     if (!(p.dbg & 1) && !mbar_wait(&full_bar[stage], phase, p.err_flag)) { ok = false; break; }
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
                     const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
                     uint64_t da = desc_tmpl | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
                     uint64_t db = desc_tmpl | (uint64_t)(((a_addr + a_bytes) & 0x3FFFFu) >> 4);
+                    // (two-term weights: each CTA's B tile is [BN/2 hi rows | BN/2 lo rows], one MMA of N = 2*BN)
                     for (int k = 0; k < ((p.dbg & 2) ? 0 : ksteps); ++k, da += 2, db += 2)
                         umma_bf16_pair(tmem_acc, da, db, p.idesc, (uint32_t)(kb | k));
                     umma_commit_pair(&empty_bar[stage]);     // both CTAs' producers may refill the stage
@@ -224,9 +227,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
 
 bool conv_pair_eligible(const ConvArgs& a) {
     if (getenv("RTOD_TC_NO_PAIR")) return false;
-    if (a.Cout_pad % 256 != 0 || a.out.fp32 || a.w_split) return false;      // two-term weights: one-CTA kernel only
+    if (a.Cout_pad % 128 != 0 || a.out.fp32) return false;
+    const int BN = (a.Cout_pad % 256 == 0 && !a.w_split) ? 256 : 128; // N tile of the pair (each CTA loads half of it)
+    if (BN == 128 && getenv("RTOD_TC_NO_PAIR128")) return false;
     const long long m_tiles = ((long long)a.B * a.out.H * a.out.W + kBM - 1) / kBM;
-    return ((m_tiles + 1) / 2) * (a.Cout_pad / 256) >= 60;          // enough pair tiles to fill 74 SM pairs
+    return ((m_tiles + 1) / 2) * (a.Cout_pad / BN) >= 60;           // enough pair tiles to fill 74 SM pairs
 }
 
 int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
@@ -239,16 +244,18 @@ int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
         if (rc) return rc;
     }
     ConvTcParams& p = launch->p;
-    const int BK = pick_bk(a.Cin), BN = 256;
+    const int BK = pick_bk(a.Cin), BN = (a.Cout_pad % 256 == 0 && !a.w_split) ? 256 : 128;   // (two-term weights: N = 2*BN)
     const long long M = (long long)a.B * a.out.H * a.out.W;
     p.bias = a.bias; p.err_flag = err_flag; p.out_fp32 = 0; p.M = (int)M; p.Cout = a.Cout; p.leaky = a.leaky;
     p.ks = a.ks; p.cchunks = a.Cin / BK; p.BK = BK; p.BN = BN;
     p.Ho = a.out.H; p.Wo = a.out.W; p.stride = a.stride; p.pad = a.pad;
-    p.tmem_cols = 512; p.has_res = a.res != nullptr; p.ecols = 64; p.b_resident = 0; p.stage_bufs = 2;
+    p.w_cat = a.w_split ? 1 : 0;
+    p.acc_cols = BN << p.w_cat; p.lo_col = BN / 2; p.subs = 1;
+    p.tmem_cols = 2 * p.acc_cols; p.has_res = a.res != nullptr; p.ecols = 64; p.b_resident = 0; p.stage_bufs = 2;
     p.dbg = (getenv("RTOD_PAIR_MODE") ? atoi(getenv("RTOD_PAIR_MODE")) : 0) | (getenv("RTOD_CLK_DBG") ? 8 : 0);
-    p.f16 = a.in.f16; p.w_split = 0; p.cout_pad = a.Cout_pad;
-    p.idesc = umma_idesc(p.f16, 256, BN);               // M = 256 per pair, N = 256
-    const uint32_t stage_bytes = (uint32_t)(kBM + BN / 2) * BK * 2;
+    p.f16 = a.in.f16; p.w_split = a.w_split; p.cout_pad = a.Cout_pad;
+    p.idesc = umma_idesc(p.f16, 256, p.acc_cols);       // M = 256 per pair
+    const uint32_t stage_bytes = (uint32_t)(kBM + ((BN / 2) << a.w_split)) * BK * 2;
     p.epi_warps = kEpilogueWarps;
     if (const char* e = getenv("RTOD_TC_SBUFS")) p.stage_bufs = atoi(e) == 1 ? 1 : 2;
     const uint32_t fixed = 1024 + kEpilogueWarps * p.stage_bufs * kEpiSlice + 512;
@@ -263,7 +270,7 @@ int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     store_fastdiv(p.fd_wo, (uint32_t)a.out.W);
     store_fastdiv(p.fd_howo, (uint32_t)(a.out.W * a.out.H));
     launch->patch = 2;
-    launch->choice = ConvTcChoice{1, 0, p.stage_bufs, 1, 256, 1, 8, 1};
+    launch->choice = ConvTcChoice{1, 0, p.stage_bufs, 1, BN, 1, 8, 1};
     p.split_k = 1; p.split_shift = 0; p.split_scratch = nullptr; p.split_count = nullptr;
     launch->smem_bytes = stages * stage_bytes + fixed;
     RTOD_CUDA_OK(cudaFuncSetAttribute(conv_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -315,7 +322,7 @@ int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     }
     if (r != CUDA_SUCCESS) return fail(RTOD_ERR_CUDA, "cuTensorMapEncode (pair activations) failed: %d", (int)r);
     {
-        const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.Cout_pad};
+        const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)(a.Cout_pad << a.w_split)};
         const cuuint64_t strides[1] = {(cuuint64_t)a.K * 2};
         const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(BN / 2)};
         r = encode_tiled(&p.tmB, h16_tmap_type(a.in.f16), 2, const_cast<void*>(a.w), dims, strides,

@@ -41,7 +41,7 @@ namespace rtod {
 namespace {
 
 constexpr int kFirstEpiWarp = 4;                // warps 0-3: TMA producer A, MMA issuer, TMA producer B, 2nd producer A
-constexpr int threads_for(int epi_warps) { return 32 * (kFirstEpiWarp + epi_warps); }
+constexpr int threads_for(int epi_warps, int subs = 1) { return 32 * (kFirstEpiWarp + epi_warps) * subs; }
 constexpr uint32_t kResidentLimit = 100 * 1024; // largest weight matrix kept resident in shared memory
 
 // =============================================================================================
@@ -49,13 +49,23 @@ constexpr uint32_t kResidentLimit = 100 * 1024; // largest weight matrix kept re
 // weight tile in L2).  The accumulator is double-buffered in TMEM, so the epilogue of tile i runs
 // while the tensor core already works on tile i+1, and the TMA producer runs ahead across tile
 // boundaries as far as the shared-memory ring allows.
-template <int kEpiWarps, bool kF16>
-__global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+// kSubs = 2 ("dual pipeline"): one CTA per SM holds TWO complete warp sets (producers, MMA issuer, epilogue warps,
+// operand ring, barriers, TMEM accumulators) that walk alternate tiles and SHARE one resident copy of the weights.
+// The thin early layers need several concurrent pipelines per SM to cover the load latency (a lone MMA / producer
+// thread retires ~one dependent instruction per 5 cycles), but two CTAs would each need their own weight copy:
+// with two-term weights (74 KB for 32 -> 64 3x3) that no longer fits, the weights go back to a per-tile ring and
+// the layer becomes bound by L2 -> SM traffic (measured: 427 us instead of 246 us).
+template <int kEpiWarps, bool kF16, int kSubs>
+__global__ void __launch_bounds__(threads_for(kEpiWarps, kSubs), (kEpiWarps == 4 && kSubs == 1) ? 3 : 1)
+conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kWarpsPerSub = kFirstEpiWarp + kEpiWarps;
+    const int sub = kSubs == 1 ? 0 : (int)(threadIdx.x >> 5) / kWarpsPerSub;       // which pipeline this warp belongs to
+    const int warp = (int)(threadIdx.x >> 5) - sub * kWarpsPerSub, lane = threadIdx.x & 31;
+    const int first_item = (int)blockIdx.x * kSubs + sub, item_step = (int)gridDim.x * kSubs;
 #ifdef RTOD_TC_TRACE
     long long dbg_c0 = 0;
     unsigned long long dbg_t0 = 0;
@@ -68,20 +78,24 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
     // weight tile of one k-block: BN rows, twice that (hi rows, then lo rows) for split weights
     const uint32_t a_bytes = kBM * row_bytes, b_half = (uint32_t)p.BN * row_bytes, b_bytes = b_half << p.w_split;
     const uint32_t stage_bytes = a_bytes + (p.b_resident ? 0u : b_bytes);
-    // ring stages hold {A, B} tiles, or A tiles only when the whole weight matrix is resident
-    uint8_t* b_resident = smem + (size_t)p.stages * stage_bytes;         // [num_kb][BN x BK] iff p.b_resident
-    uint8_t* epi_stage = b_resident + (p.b_resident ? (size_t)p.ks * p.ks * p.cchunks * b_bytes : 0);
-    // [kEpiWarps][stage_bufs][kEpiSlice] epilogue staging slices (output, and shortcut operand in place)
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + (size_t)kEpiWarps * p.stage_bufs * kEpiSlice);
+    // ring stages (one ring per pipeline) hold {A, B} tiles, or A tiles only when the whole weight matrix is resident
+    uint8_t* ring = smem + (size_t)sub * p.stages * stage_bytes;
+    uint8_t* b_resident = smem + (size_t)kSubs * p.stages * stage_bytes; // [num_kb][BN x BK] iff p.b_resident (shared)
+    uint8_t* epi_all = b_resident + (p.b_resident ? (size_t)p.ks * p.ks * p.cchunks * b_bytes : 0);
+    // [kSubs][kEpiWarps][stage_bufs][kEpiSlice] epilogue staging slices (output, and shortcut operand in place)
+    uint8_t* epi_stage = epi_all + (size_t)sub * kEpiWarps * p.stage_bufs * kEpiSlice;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_all + (size_t)kSubs * kEpiWarps * p.stage_bufs * kEpiSlice);
+    const int bars_per_sub = 2 * p.stages + 4 + 2 * kEpiWarps;
+    uint64_t* full_bar = bars + sub * bars_per_sub;
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* acc_full = empty_bar + p.stages;          // [2] MMA -> epilogue
     uint64_t* acc_empty = acc_full + 2;                 // [2] epilogue -> MMA
     uint64_t* res_full = acc_empty + 2;                 // [kEpiWarps][2] TMA (shortcut operand) -> epilogue warp
-    uint64_t* wres_bar = res_full + 2 * kEpiWarps;      // [1] resident weights have landed
+    uint64_t* wres_bar = bars + kSubs * bars_per_sub;   // [1] resident weights have landed (shared)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
-    int* s_last = reinterpret_cast<int*>(tmem_slot + 1);       // split-K: this CTA finishes the current tile
+    int* s_last = reinterpret_cast<int*>(tmem_slot + 1) + sub;  // split-K: this CTA finishes the current tile
 #ifdef RTOD_TC_TRACE
-    unsigned long long* s_ts = reinterpret_cast<unsigned long long*>(tmem_slot + 4);   // [0] = entry, [1..7] stamps
+    unsigned long long* s_ts = reinterpret_cast<unsigned long long*>(tmem_slot + 4);   // [0] = entry, [1..7] stamps (pipeline 0)
     if (threadIdx.x == 0) {
         for (int i = 1; i < 8; ++i) s_ts[i] = 0;
         s_ts[0] = global_timer_ns();
@@ -97,13 +111,13 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
     const int n_items = p.total_tiles << p.split_shift;
     const int kb_per = (num_kb + p.split_k - 1) >> p.split_shift;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && lane == 0 && sub == 0) {
         prefetch_tmap(&p.tmA);
         prefetch_tmap(&p.tmB);
         prefetch_tmap(&p.tmOut);
         if (p.has_res) prefetch_tmap(&p.tmRes);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == 1 && lane == 0) {                       // every pipeline initialises its own barriers
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], p.b_resident ? 1 : 2);      // one arrive.expect_tx per producer thread
             mbar_init(&empty_bar[s], 1);
@@ -113,16 +127,16 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
             mbar_init(&acc_empty[b], kEpiWarps);
         }
         for (int b = 0; b < 2 * kEpiWarps; ++b) mbar_init(&res_full[b], 1);
-        mbar_init(wres_bar, 1);
+        if (sub == 0) mbar_init(wres_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kFirstEpiWarp) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp == kFirstEpiWarp && sub == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);   // all pipelines' accumulators
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot + (uint32_t)(sub * 2 * p.acc_cols);
     if (threadIdx.x == 0) { TRACE_STAMP(1); }
-    if (p.pf_bytes && warp == 2 && elect_one()) {
+    if (p.pf_bytes && warp == 2 && sub == 0 && elect_one()) {
         // small batches stream every weight from HBM once per forward and the k-loops are latency-bound: pull
         // the NEXT layer's weights into L2 now (they do not depend on the previous layer, so before the wait)
         const unsigned long long per = ((p.pf_bytes + gridDim.x - 1) / gridDim.x + 127ull) & ~127ull;
@@ -157,7 +171,7 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
             const int cin = p.cchunks * p.BK;
             TRACE_DECL(dbg_wait);
             TRACE_T0(dbg_start);
-            for (int item = blockIdx.x; ok && item < n_items; item += gridDim.x) {
+            for (int item = first_item; ok && item < n_items; item += item_step) {
                 const int tile = item >> p.split_shift;
                 const int kb0 = (item & (p.split_k - 1)) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
                 int kb = 0;
@@ -184,7 +198,7 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                         TRACE_T0(w0);
                         if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag)) { ok = false; break; }
                         TRACE_ADD(dbg_wait, w0);
-                        uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
+                        uint8_t* a_dst = ring + (size_t)stage * stage_bytes;
                         mbar_expect_tx(&full_bar[stage], a_bytes);
                         if (p.ks > 1)
                             tma_load_im2col_4d(a_dst, &p.tmA, &full_bar[stage], c0, ow, oh, on, (uint16_t)kx, (uint16_t)ky);
@@ -200,32 +214,34 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
 #ifdef RTOD_TC_TRACE
             if ((p.dbg & 16) && blockIdx.x == 0)
                 printf("  tc producer %d: total %lld clk, waiting for empty %lld, tiles %d x %d k-blocks, stages %d, grid %d\n", me,
-                       clock64() - dbg_start, dbg_wait, (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x, num_kb, p.stages, (int)gridDim.x);
+                       clock64() - dbg_start, dbg_wait, (p.total_tiles + item_step - 1) / item_step, num_kb, p.stages, (int)gridDim.x);
 #endif
         }
     } else if (warp == 2) {
         // ================= TMA producer B: weight tiles (ring), or the whole matrix once =================
         if (elect_one()) {
-            if (p.b_resident) {                  // single N tile: the whole [BN x K] weight matrix, once
+            if (p.b_resident) {                  // single N tile: the whole [BN x K] weight matrix, once per CTA
+              if (sub == 0) {
                 mbar_expect_tx(wres_bar, (uint32_t)num_kb * b_bytes);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     tma_load_2d(b_resident + (size_t)kb * b_bytes, &p.tmB, wres_bar, kb * p.BK, 0);
                     if (p.w_split) tma_load_2d(b_resident + (size_t)kb * b_bytes + b_half, &p.tmB, wres_bar, kb * p.BK, p.cout_pad);
                 }
+              }
             } else {
                 int stage = 0;
                 uint32_t phase = 0;
                 bool ok = true;
-                for (int item = blockIdx.x; ok && item < n_items; item += gridDim.x) {
+                for (int item = first_item; ok && item < n_items; item += item_step) {
                     const int tile = item >> p.split_shift;
                     const int kb0 = (item & (p.split_k - 1)) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
                     const int n0 = (int)fast_div((uint32_t)tile, p.fd_mtiles) * p.BN;
                     for (int k0 = kb0 * p.BK; k0 < kb1 * p.BK; k0 += p.BK) {
                         if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag)) { ok = false; break; }
                         mbar_expect_tx(&full_bar[stage], b_bytes);
-                        tma_load_2d(smem + (size_t)stage * stage_bytes + a_bytes, &p.tmB, &full_bar[stage], k0, n0);
+                        tma_load_2d(ring + (size_t)stage * stage_bytes + a_bytes, &p.tmB, &full_bar[stage], k0, n0);
                         if (p.w_split)
-                            tma_load_2d(smem + (size_t)stage * stage_bytes + a_bytes + b_half, &p.tmB, &full_bar[stage], k0, p.cout_pad + n0);
+                            tma_load_2d(ring + (size_t)stage * stage_bytes + a_bytes + b_half, &p.tmB, &full_bar[stage], k0, p.cout_pad + n0);
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1u;
@@ -242,13 +258,13 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
             bool ok = true;
             int local = 0;
             const uint64_t desc_tmpl = smem_desc(0u, row_bytes);
-            const uint32_t ring_base = smem_u32(smem), wres_base = smem_u32(b_resident);
+            const uint32_t ring_base = smem_u32(ring), wres_base = smem_u32(b_resident);
             const int ksteps = p.BK / 16;
             TRACE_DECL(dbg_wacc);
             TRACE_DECL(dbg_wfull);
             TRACE_T0(dbg_start);
             if (p.b_resident) ok = mbar_wait(wres_bar, 0u, p.err_flag);
-            for (int item = blockIdx.x; ok && item < n_items; item += gridDim.x, ++local) {
+            for (int item = first_item; ok && item < n_items; item += item_step, ++local) {
                 const int kb0 = (item & (p.split_k - 1)) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
                 const int buf = local & 1;
                 const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
@@ -256,7 +272,7 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                 if (!mbar_wait(&acc_empty[buf], acc_phase ^ 1u, p.err_flag)) break;   // epilogue drained it
                 TRACE_ADD(dbg_wacc, w0);
                 tc_fence_after();
-                const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.BN);
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.acc_cols);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     TRACE_T0(w1);
                     if (!mbar_wait(&full_bar[stage], phase, p.err_flag)) { ok = false; break; }
@@ -268,16 +284,9 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                     const uint32_t b_addr = p.b_resident ? wres_base + (uint32_t)kb * b_bytes : a_addr + a_bytes;
                     uint64_t da = desc_tmpl | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
                     uint64_t db = desc_tmpl | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
-                    if (!p.w_split) {
-                        for (int k = 0; k < ksteps; ++k, da += 2, db += 2)      // +32 bytes per K=16 step
-                            umma_bf16(tmem_acc, da, db, p.idesc, (uint32_t)((kb - kb0) | k));
-                    } else {                                     // A * (W_hi + W_lo): the small term first
-                        const uint64_t lo_off = (uint64_t)(b_half >> 4);
-                        for (int k = 0; k < ksteps; ++k, da += 2, db += 2) {
-                            umma_bf16(tmem_acc, da, db + lo_off, p.idesc, (uint32_t)((kb - kb0) | k));
-                            umma_bf16(tmem_acc, da, db, p.idesc, 1u);
-                        }
-                    }
+                    // (two-term weights: the B tile is [BN hi rows | BN lo rows], one MMA of N = 2*BN)
+                    for (int k = 0; k < ksteps; ++k, da += 2, db += 2)      // +32 bytes per K=16 step
+                        umma_bf16(tmem_acc, da, db, p.idesc, (uint32_t)((kb - kb0) | k));
                     umma_commit(&empty_bar[stage]);          // frees the stage when the MMAs retire
                     if (++stage == p.stages) {
                         stage = 0;
@@ -306,7 +315,7 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
             conv_epilogue_split<kEpiWarps, kF16>(
                 p, tmem_base, acc_full, epi_stage, res_full, s_last, warp - kFirstEpiWarp, lane,
                 [&](int local, int& tile, int& slice_k) {
-                    const int item = (int)blockIdx.x + local * (int)gridDim.x;
+                    const int item = first_item + local * item_step;
                     tile = item >> p.split_shift;
                     slice_k = item & (p.split_k - 1);
                     return item < n_items;
@@ -314,10 +323,10 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                 origin, release);
         else
             conv_epilogue<kEpiWarps, kF16>(p, tmem_base, acc_full, epi_stage, res_full, warp - kFirstEpiWarp, lane,
-                                     (int)blockIdx.x, (int)gridDim.x, origin, release);
+                                     first_item, item_step, origin, release);
     }
 
-    if (warp == kFirstEpiWarp && lane == 0) { TRACE_STAMP(6); }
+    if (warp == kFirstEpiWarp && lane == 0 && sub == 0) { TRACE_STAMP(6); }
     __syncthreads();
 #ifdef RTOD_TC_TRACE
     if ((p.dbg & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -329,9 +338,9 @@ __global__ void __launch_bounds__(threads_for(kEpiWarps), kEpiWarps == 4 ? 3 : 1
                global_timer_ns() - s_ts[0]);
     }
 #endif
-    if (warp == kFirstEpiWarp) {
+    if (warp == kFirstEpiWarp && sub == 0) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+        tmem_dealloc(*tmem_slot, (uint32_t)p.tmem_cols);
     }
 }
 
@@ -389,6 +398,9 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
     const int BK = pick_bk(a.Cin);
     int BN = a.Cout_pad < 256 ? a.Cout_pad : 256;       // widest tile the single-CTA MMA supports
     if (a.Cout_pad % BN != 0) BN = 128;
+    // two-term weights always run as one concatenated MMA of N = 2*BN <= 256 (w_cat): the hi and lo products are
+    // added in the epilogue, so the rounding -- unlike the tile shape -- must not depend on the configuration
+    if (a.w_split && BN > 128) BN = 128;
     {   // small batches: a layer must still spread over the 148 SMs -> narrower N tiles
         const long long m_tiles = ((long long)a.B * a.out.H * a.out.W + kBM - 1) / kBM;
         while (BN > 32 && m_tiles * (a.Cout_pad / BN) < 120 && a.Cout_pad % (BN / 2) == 0) BN /= 2;
@@ -398,7 +410,7 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
         if (v >= 32 && v <= BN && a.Cout_pad % v == 0) BN = v;
     }
     if (force && force->bn) {
-        if (force->bn > 256 || force->bn < 32 || a.Cout_pad % force->bn != 0 || (force->bn & (force->bn - 1)))
+        if (force->bn > (a.w_split ? 128 : 256) || force->bn < 32 || a.Cout_pad % force->bn != 0 || (force->bn & (force->bn - 1)))
             return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: forced N tile %d not applicable", force->bn);
         BN = force->bn;
     }
@@ -419,14 +431,19 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
     p.Wo = a.out.W;
     p.stride = a.stride;
     p.pad = a.pad;
+    p.w_cat = a.w_split ? 1 : 0;
+    p.acc_cols = BN << p.w_cat;
+    p.lo_col = BN;
+    // dual pipeline (two warp sets sharing resident weights in one CTA per SM): asked for by the autotuner / tests
+    // through `force`, or by the heuristic for resident-weight layers whose weights are too large for two CTAs
+    int subs = force ? (force->subs == 2 ? 2 : 1) : 1;
     int cols = 32;
-    while (cols < 2 * BN) cols <<= 1;                    // two accumulator buffers
-    p.tmem_cols = cols;
+    while (cols < 2 * p.acc_cols) cols <<= 1;            // two accumulator buffers (per pipeline)
     p.f16 = a.in.f16;
     p.w_split = a.w_split;
     p.cout_pad = a.Cout_pad;
     // c_format F32 (bit 4), a/b format (bits 7, 10: 0 = F16, 1 = BF16), K-major both, N>>3 at 17, M>>4 at 24
-    p.idesc = umma_idesc(p.f16, kBM, BN);
+    p.idesc = umma_idesc(p.f16, kBM, p.acc_cols);
     const uint32_t stage_bytes = (uint32_t)(kBM + (BN << a.w_split)) * BK * 2;
     p.has_res = a.res != nullptr;
     // ---- shared-memory plan --------------------------------------------------------------------
@@ -437,7 +454,9 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
     const uint32_t w_bytes = (uint32_t)(BN << a.w_split) * a.K * 2;
     const bool may_reside = a.Cout_pad == BN && w_bytes <= kResidentLimit && getenv("RTOD_TC_NO_RESIDENT") == nullptr;
     const uint32_t a_stage = (uint32_t)kBM * BK * 2;
-    int max_ctas = 512 / cols;
+    if (subs == 2 && (2 * cols > 512 || a.Cout_pad != BN || w_bytes > 2 * kResidentLimit || getenv("RTOD_TC_NO_RESIDENT")))
+        return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: dual pipeline needs resident weights and 2 x %d TMEM columns", cols);
+    int max_ctas = subs == 2 ? 1 : 512 / cols;
     if (const char* e = getenv("RTOD_TC_CTAS")) { const int v = atoi(e); if (v >= 1 && v < max_ctas) max_ctas = v; }
     if (max_ctas > 3) max_ctas = 3;                      // measured: 3 beats 2 and 4 on the 208x208 layers
     int ctas_per_sm = 1, stages = 0;
@@ -451,21 +470,21 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
     for (int ctas = max_ctas; ctas >= 1 && stages == 0; --ctas) {
         if (force && force->ctas != ctas) continue;
         const uint32_t cap = ctas == 1 ? kSmemLimit : (227u * 1024u) / ctas - 2048u;
-        int ew = (ctas == 1 && BN >= 128) ? 8 : 4;
-        if (env_ew && (atoi(env_ew) == 4 || (atoi(env_ew) == 8 && BN >= 128))) ew = atoi(env_ew);
+        int ew = (ctas == 1 && BN >= 128 && subs == 1) ? 8 : 4;
+        if (env_ew && (atoi(env_ew) == 4 || (atoi(env_ew) == 8 && BN >= 128 && subs == 1))) ew = atoi(env_ew);
         if (force && force->ew) {
-            if (force->ew == 8 && BN < 128) continue;
+            if (force->ew == 8 && (BN < 128 || subs == 2)) continue;
             ew = force->ew;
         }
         for (int opt = 0; opt < 4 && stages == 0; ++opt) {
-            const bool resident = may_reside && (opt & 1) == 0;
+            const bool resident = (may_reside || subs == 2) && (opt & 1) == 0;      // (dual: weights up to 2 x the limit)
             const int sbufs = (opt & 2) ? 1 : 2;
-            if ((opt & 1) && may_reside == false) continue;
+            if ((opt & 1) && (may_reside == false || subs == 2)) continue;
             if (force && (force->resident != (resident ? 1 : 0) || force->sbufs != sbufs)) continue;
             if (env_sb && atoi(env_sb) != sbufs) continue;
-            const uint32_t fx = 1024 + ew * sbufs * kEpiSlice + 512 + (resident ? w_bytes : 0);
-            const uint32_t sb = resident ? a_stage : stage_bytes;
-            const int want = ctas == 1 ? 2 : 3;
+            const uint32_t fx = 1024 + subs * ew * sbufs * kEpiSlice + 512 * subs + (resident ? w_bytes : 0);
+            const uint32_t sb = (resident ? a_stage : stage_bytes) * subs;         // one ring per pipeline
+            const int want = (ctas == 1 && subs == 1) ? 2 : 3;
             if (fx + want * sb > cap) continue;
             ctas_per_sm = ctas;
             epi_warps = ew;
@@ -478,6 +497,8 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
         }
     }
     p.epi_warps = epi_warps;
+    p.subs = subs;
+    p.tmem_cols = cols * subs;
     {   // split-K: a function of the layer shape only (conv_split_factor) -- never of timing -- so that two plans
         // of the same network always add the partial sums in the same order; tests may force a factor
         int split = force && force->split > 0 ? force->split : conv_split_factor(a);
@@ -489,12 +510,13 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
                 (unsigned long long)tiles * split * kBM * BN * 4ull > a.split_scratch_bytes)
                 return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: split-K %d not applicable", split);
         }
+        if (split > 1 && subs == 2) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: no split-K on the dual pipeline");
         p.split_k = split;
         p.split_shift = split == 8 ? 3 : (split == 4 ? 2 : (split == 2 ? 1 : 0));
         p.split_scratch = a.split_scratch;
         p.split_count = a.split_count;
     }
-    launch->choice = ConvTcChoice{ctas_per_sm, p.b_resident, p.stage_bufs, 0, BN, p.split_k, epi_warps, p.a_producers};
+    launch->choice = ConvTcChoice{ctas_per_sm, p.b_resident, p.stage_bufs, 0, BN, p.split_k, epi_warps, p.a_producers, subs};
     // im2col issue costs a thread ~350 cycles: two alternating A producers when a k-block's MMAs take less
     p.a_producers = (a.ks > 1 && (BK / 16) * (BN / 2) < 350 && getenv("RTOD_TC_ONE_A") == nullptr) ? 2 : 1;
     if (force && force->ap) {
@@ -511,7 +533,7 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
         if (v >= 2 && v < stages) stages = v;
     }
     if (stages < 2) stages = 2;
-    p.stages = stages;
+    p.stages = stages;                                   // per pipeline (stage_bytes_eff covers all pipelines)
     p.m_tiles = (int)((M + kBM - 1) / kBM);
     p.total_tiles = p.m_tiles * (a.Cout_pad / BN);
     store_fastdiv(p.fd_mtiles, (uint32_t)p.m_tiles);
@@ -520,7 +542,8 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
     launch->smem_bytes = stages * stage_bytes_eff + fixed;
     {
         const int items = p.total_tiles * p.split_k;
-        launch->grid = dim3((unsigned)(items < kNumSMs * ctas_per_sm ? items : kNumSMs * ctas_per_sm), 1, 1);
+        const int ctas_wanted = (items + subs - 1) / subs;
+        launch->grid = dim3((unsigned)(ctas_wanted < kNumSMs * ctas_per_sm ? ctas_wanted : kNumSMs * ctas_per_sm), 1, 1);
     }
 
     // ---- A ----
@@ -591,10 +614,12 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
         }
     }
     // per device and cheap: set on every prepare (a process may drive several GPUs)
-    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<4, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<8, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<4, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<4, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<8, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RTOD_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<4, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return RTOD_OK;
 }
 
@@ -605,7 +630,7 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
 int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cudaStream_t stream) {
     if (const char* f = getenv("RTOD_TC_FORCE")) {       // tests: "pair,bn,ctas,resident,sbufs" -> exactly that candidate
         ConvTcChoice c{};
-        if (sscanf(f, "%d,%d,%d,%d,%d,%d", &c.pair, &c.bn, &c.ctas, &c.resident, &c.sbufs, &c.split) >= 5 &&
+        if (sscanf(f, "%d,%d,%d,%d,%d,%d,%d", &c.pair, &c.bn, &c.ctas, &c.resident, &c.sbufs, &c.split, &c.subs) >= 5 &&
             conv_tc_prepare(a, err_flag, launch, &c) == RTOD_OK)
             return RTOD_OK;                              // (a candidate that does not fit falls through to the default)
     }
@@ -636,14 +661,16 @@ int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cud
         for (int ctas = 3; ctas >= 1; --ctas)
             for (int resident = 1; resident >= 0; --resident)
                 for (int sbufs = 2; sbufs >= 1; --sbufs) {
-                    if (pair && (bn != 256 || ctas != 1 || resident != 0 || sbufs != 2)) continue;   // one pair configuration
+                    if (pair && (bn != 256 || ctas != 1 || resident != 0 || sbufs != 2)) continue;   // one pair configuration (its N tile follows Cout)
                     if (!pair && bn > a.Cout_pad) continue;
                     if (sbufs == 1 && a.res) continue;       // the shortcut operand is prefetched into the 2nd slice
                   for (int ew = 4; ew <= 8; ew += 4)
-                   for (int ap = 1; ap <= 2; ++ap) {
-                    if (pair && (ew != 8 || ap != 1)) continue;
+                   for (int ap = 1; ap <= 2; ++ap)
+                    for (int subs = 1; subs <= 2; ++subs) {
+                    if (pair && (ew != 8 || ap != 1 || subs != 1)) continue;
                     if (!pair && ((ew == 8 && (bn < 128 || ctas == 3)) || (ap == 2 && a.ks == 1))) continue;
-                    const ConvTcChoice c{ctas, resident, sbufs, pair, bn, 0, pair ? 0 : ew, pair ? 0 : ap};
+                    if (subs == 2 && (ctas != 1 || ew != 4 || !resident)) continue;      // dual pipeline: one CTA, shared resident weights
+                    const ConvTcChoice c{ctas, resident, sbufs, pair, bn, 0, pair ? 0 : ew, pair ? 0 : ap, subs};
                     cand = ConvTcLaunch{};
                     if (conv_tc_prepare(a, err_flag, &cand, &c) != RTOD_OK) continue;      // does not fit / apply
                     float ms;
@@ -659,9 +686,10 @@ int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cud
     if (rc) return rc;
     *launch = best;
     if (getenv("RTOD_TC_TUNE_DBG"))
-        fprintf(stderr, "conv_tc_autotune: M %d Cin %d Cout %d ks %d s %d -> %s BN %d ctas %d resident %d sbufs %d split %d epi %d aprod %d stages %d (%.1f us)\n",
+        fprintf(stderr, "conv_tc_autotune: M %d Cin %d Cout %d ks %d s %d -> %s BN %d ctas %d resident %d sbufs %d split %d epi %d aprod %d stages %d pipelines %d (%.1f us)\n",
                 a.B * a.out.H * a.out.W, a.Cin, a.Cout, a.ks, a.stride, best.patch == 2 ? "pair" : "tc", best.choice.bn, best.choice.ctas,
-                best.choice.resident, best.choice.sbufs, best.choice.split, best.p.epi_warps, best.p.a_producers, best.p.stages, best_ms * 1e3f);
+                best.choice.resident, best.choice.sbufs, best.choice.split, best.p.epi_warps, best.p.a_producers, best.p.stages,
+                best.p.subs, best_ms * 1e3f);
     return RTOD_OK;
 }
 
@@ -669,7 +697,7 @@ int conv_tc_launch(const ConvTcLaunch& launch, cudaStream_t stream) {
     if (launch.patch == 2) return conv_pair_launch(launch, stream);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = launch.grid;
-    cfg.blockDim = dim3((unsigned)threads_for(launch.p.epi_warps), 1, 1);
+    cfg.blockDim = dim3((unsigned)threads_for(launch.p.epi_warps, launch.p.subs), 1, 1);
     cfg.dynamicSmemBytes = launch.smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -678,11 +706,13 @@ int conv_tc_launch(const ConvTcLaunch& launch, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     if (launch.p.f16) {
-        if (launch.p.epi_warps == 8) RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<8, true>, launch.p));
-        else RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<4, true>, launch.p));
+        if (launch.p.subs == 2) RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<4, true, 2>, launch.p));
+        else if (launch.p.epi_warps == 8) RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<8, true, 1>, launch.p));
+        else RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<4, true, 1>, launch.p));
     } else {
-        if (launch.p.epi_warps == 8) RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<8, false>, launch.p));
-        else RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<4, false>, launch.p));
+        if (launch.p.subs == 2) RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<4, false, 2>, launch.p));
+        else if (launch.p.epi_warps == 8) RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<8, false, 1>, launch.p));
+        else RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<4, false, 1>, launch.p));
     }
     return RTOD_OK;
 }

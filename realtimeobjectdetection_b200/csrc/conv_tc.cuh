@@ -35,6 +35,11 @@ struct alignas(64) ConvTcParams {
     int w_split;                // 1: weights are hi + lo (two fp16 terms, rows [Cout_pad, 2*Cout_pad) of tmB hold lo):
                                 // two MMAs per K step, for layers whose tensor time hides behind their HBM time
     int cout_pad;               // row offset of the lo half in tmB
+    int w_cat;                  // two-term weights as ONE MMA of N = 2*BN per K step (hi and lo accumulate in separate
+                                // TMEM columns, added by the epilogue): half the MMA instructions; needs 2*BN <= 256
+    int acc_cols;               // TMEM columns of one accumulator buffer: BN << w_cat
+    int subs;                   // pipelines (warp sets) per CTA: 1, or 2 sharing the resident weights
+    int lo_col;                 // column distance from a value's hi term to its lo term (w_cat): BN, pair kernel BN / 2
     int split_k, split_shift;   // K slices per output tile (power of two, 1 = off) and log2 of it
     float* split_scratch;       // [total_tiles][split_k][128][BN] fp32 partial accumulators
     int* split_count;           // [total_tiles] arrival counters (zero between forwards)
@@ -46,6 +51,7 @@ struct ConvTcChoice {           // one launch configuration of conv_tc_kernel (o
     int bn;                     // N tile (0 = heuristic)
     int split;                  // K slices per tile (0 = by shape)
     int ew, ap;                 // epilogue warps (4 / 8), activation producer threads (1 / 2); 0 = heuristic
+    int subs;                   // 2 = dual pipeline (two warp sets sharing resident weights in one CTA); 0 / 1 = single
 };
 
 struct ConvTcLaunch {           // host side: kernel parameters + launch geometry

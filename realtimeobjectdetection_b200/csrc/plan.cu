@@ -182,7 +182,7 @@ int infer_shapes(RtodPlan& p) {
 }
 
 // Two-term weights (w = hi + lo in fp16, two MMAs per K step) where the extra tensor work hides behind the
-// layer's own HBM time: arithmetic intensity 2*M*N*K / bytes below roughly the machine's ridge (211 FLOP/B
+// layer's own memory time: arithmetic intensity 2*M*N*K / bytes below the machine's ridge (211 FLOP/B
 // measured), and only for layers with many output elements -- every rounded element contributes equally to the
 // prediction error of a deep network, so the large early layers dominate it ("numerics").
 // A function of the layer shape only.
@@ -191,7 +191,7 @@ int choose_w_split(const RtodPlan& p, const Node& nd) {
     const double in_px = (double)(nd.d.stride * nd.d.stride);            // input pixels read per output pixel
     const double bytes = 2.0 * (in_px * nd.Cin + nd.d.filters * (nd.res_src >= -1 ? 2.0 : 1.0));
     const double ai = 2.0 * nd.d.filters * nd.K / bytes;
-    double ai_max = 240.0, min_elems = 300000.0;
+    double ai_max = 200.0, min_elems = 300000.0;
     if (const char* e = getenv("RTOD_WSPLIT_AI")) ai_max = atof(e);
     if (const char* e = getenv("RTOD_WSPLIT_ELEMS")) min_elems = atof(e);
     return ai < ai_max && (double)nd.H * nd.W * nd.d.filters >= min_elems ? 1 : 0;
@@ -575,8 +575,8 @@ static int run_forward(RtodPlan* p, const float* x, float* pred, int train, cuda
         if (p->nodes[i].d.type == RTOD_LAYER_CONV && !p->nodes[i].weights_set)
             return fail(RTOD_ERR_STATE, "rtod_plan_forward: convolution %d has no weights", i);
     int rc;
-    if (ev) RTOD_CUDA_OK(cudaEventRecord(ev[0], stream));
     if (p->input_buf >= 0 && (rc = launch_nchw_to_nhwc(x, p->batch, act_of(*p, kInputLayer), stream))) return rc;
+    if (ev) RTOD_CUDA_OK(cudaEventRecord(ev[0], stream));              // (behind the layout conversion of a non-stem input)
     for (int i = 0; i < n; ++i) {
         Node& nd = p->nodes[i];
         if (ev && i > 0) RTOD_CUDA_OK(cudaEventRecord(ev[i], stream));
@@ -694,6 +694,21 @@ extern "C" int rtod_plan_conv_backend(const RtodPlan* p, int layer) {
     if (nd.stem) return RTOD_CONV_STEM;
     if (!nd.use_tc) return RTOD_CONV_SIMT;
     return nd.tc.patch == 2 ? RTOD_CONV_TC_PAIR : RTOD_CONV_TC;
+}
+
+extern "C" int rtod_plan_conv_config(const RtodPlan* p, int layer, int* out12) {
+    if (!p || !p->bound || !out12 || layer < 0 || layer >= (int)p->nodes.size() || p->nodes[layer].d.type != RTOD_LAYER_CONV)
+        return fail(RTOD_ERR_BAD_ARG, "rtod_plan_conv_config: bad plan, layer %d or output", layer);
+    const Node& nd = p->nodes[layer];
+    for (int i = 0; i < 12; ++i) out12[i] = 0;
+    out12[0] = rtod_plan_conv_backend(p, layer);
+    out12[10] = nd.w_split;
+    if (!nd.use_tc) return RTOD_OK;
+    const ConvTcChoice& c = nd.tc.choice;
+    out12[1] = nd.tc.p.BN; out12[2] = c.ctas; out12[3] = nd.tc.p.b_resident; out12[4] = nd.tc.p.stage_bufs;
+    out12[5] = nd.tc.p.split_k; out12[6] = nd.tc.p.epi_warps; out12[7] = nd.tc.p.a_producers; out12[8] = nd.tc.p.subs;
+    out12[9] = nd.tc.p.stages; out12[11] = (int)nd.tc.grid.x;
+    return RTOD_OK;
 }
 
 extern "C" int rtod_plan_read_layer(RtodPlan* p, int layer, float* out_nchw, void* stream) {

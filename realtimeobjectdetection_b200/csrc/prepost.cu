@@ -125,8 +125,8 @@ __global__ void rescale_boxes_kernel(const float* __restrict__ rows, int D, cons
     long long img = (long long)r[0];                                        // .long(): truncation
     img = img < 0 ? 0 : (img >= n_img ? n_img - 1 : img);                   // (index_select would raise; stay in range)
     const float w = im_dims[img * 4 + 0], h = im_dims[img * 4 + 1];
-    // torch.min(ref / dims, 1)[0] over (w, h, w, h)
-    const float sf = nan_min(__fdiv_rn(ref_dim, w), __fdiv_rn(ref_dim, h));
+    // torch.min(ref / dims, 1)[0] over (w, h, w, h); int / Tensor is Tensor.__rtruediv__ = reciprocal() * int
+    const float sf = nan_min(__fmul_rn(__frcp_rn(w), ref_dim), __fmul_rn(__frcp_rn(h), ref_dim));
     const float ox = __fdiv_rn(__fsub_rn(inp_dim, __fmul_rn(sf, w)), 2.0f);
     const float oy = __fdiv_rn(__fsub_rn(inp_dim, __fmul_rn(sf, h)), 2.0f);
     float* o = out_rows + (long long)j * 8;

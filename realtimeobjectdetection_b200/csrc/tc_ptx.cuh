@@ -188,6 +188,25 @@ static __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// v[j] += TMEM[lane][col + j], j < 32, in two 16-column loads (keeps the register peak low): the second term of
+// a two-term-weight accumulator (columns [N, 2N) of the concatenated MMA) is folded into the first
+static __device__ __forceinline__ void tmem_ld_add_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t w[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+              "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+            : "r"(taddr + (uint32_t)(half * 16)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            v[half * 16 + j] = __float_as_uint(__uint_as_float(v[half * 16 + j]) + __uint_as_float(w[j]));
+    }
+}
+
 // programmatic dependent launch: the kernel's prologue (barrier init, TMEM allocation, descriptor prefetch)
 // overlaps the tail of the previous kernel in the stream; pdl_wait() returns once that kernel has completed
 // and its writes are visible, pdl_launch_dependents() lets the next kernel start its own prologue

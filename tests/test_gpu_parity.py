@@ -157,7 +157,7 @@ def _aligned(t):
     return (t.data_ptr() + 255) // 256 * 256
 
 
-def run_block(lib, descs, x, weights, flags=0, backends=None, splits=None):
+def run_block(lib, descs, x, weights, flags=0, backends=None, splits=None, configs=None):
     """Drive the C ABI directly: plan over `descs`, input x [B,C,H,W]; returns the fp32 NCHW output
     of every layer (and appends each layer's rtod_plan_conv_backend to `backends` / rtod_plan_conv_w_split to
     `splits` if given)."""
@@ -189,6 +189,12 @@ def run_block(lib, descs, x, weights, flags=0, backends=None, splits=None):
         backends.extend(lib.rtod_plan_conv_backend(plan, i) for i in range(len(descs)))
     if splits is not None:
         splits.extend(lib.rtod_plan_conv_w_split(plan, i) for i in range(len(descs)))
+    if configs is not None:
+        for i in range(len(descs)):
+            cfg12 = (ctypes.c_int * 12)()
+            if lib.rtod_plan_conv_config(plan, i, cfg12) == 0:
+                configs.append(dict(zip(("backend", "bn", "ctas", "resident", "sbufs", "split_k", "epi_warps", "a_producers",
+                                         "pipelines", "stages", "w_split", "grid"), list(cfg12))))
     outs = []
     for i in range(len(descs)):
         c, h, w = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
@@ -289,8 +295,61 @@ def test_conv_block_two_term_weights(lib, monkeypatch, cin, cout, k, stride, H, 
     assert splits == [0]
 
 
+DUAL_CASES = [(32, 64, 3, 1, 64, 4, 64), (32, 64, 3, 2, 104, 2, 64), (64, 32, 1, 1, 48, 3, 32), (16, 32, 3, 1, 40, 2, 32),
+              (128, 64, 1, 1, 40, 3, 64), (32, 32, 3, 1, 30, 5, 32)]
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,H,batch,bn", DUAL_CASES)
+@pytest.mark.parametrize("split", [0, 1])
+@pytest.mark.parametrize("dtype,dflag", DTYPES)
+def test_conv_block_dual_pipeline(lib, monkeypatch, cin, cout, k, stride, H, batch, bn, split, dtype, dflag):
+    """two warp sets (producers, MMA issuer, epilogue, ring, accumulators) in one CTA sharing the resident weights,
+    walking alternate tiles: same result, bit for bit, as the single-pipeline configuration; odd tile counts, shortcut"""
+    if split and dtype == "bf16":
+        pytest.skip("two-term weights are an fp16 feature")
+    monkeypatch.setenv("RTOD_WSPLIT_ELEMS", "0")
+    monkeypatch.setenv("RTOD_WSPLIT_AI", "10000" if split else "0")
+    rng = np.random.RandomState(cin * 11 + cout + k + stride)
+    x = torch.from_numpy(rng.randn(batch, cin, H, H).astype(np.float32))
+    w = rand_conv(rng, cin, cout, k)
+    outs = {}
+    for sbufs in (2, 1):
+        monkeypatch.setenv("RTOD_TC_FORCE", "0,%d,1,1,%d,0,2" % (bn, sbufs))
+        cfgs = []
+        outs[sbufs] = run_block(lib, [conv_desc(cout, k, stride)], x, {0: w}, dflag, configs=cfgs)[0]
+        assert cfgs[0]["pipelines"] == 2 and cfgs[0]["resident"] == 1 and cfgs[0]["w_split"] == split, cfgs
+    monkeypatch.setenv("RTOD_TC_FORCE", "0,%d,1,0,2,0,1" % bn)
+    cfgs = []
+    single = run_block(lib, [conv_desc(cout, k, stride)], x, {0: w}, dflag, configs=cfgs)[0]
+    assert cfgs[0]["pipelines"] == 1
+    monkeypatch.delenv("RTOD_TC_FORCE")
+    ref_q = ref_block(x, w, k, stride, True, dtype, split=bool(split))
+    assert frac_within(single, ref_q, *BLOCK_TOL[dtype]) == 1.0
+    assert torch.equal(outs[2], single) and torch.equal(outs[1], single)
+
+
+def test_residual_block_dual_pipeline(lib, monkeypatch):
+    monkeypatch.setenv("RTOD_WSPLIT_ELEMS", "0")
+    monkeypatch.setenv("RTOD_WSPLIT_AI", "10000")
+    rng = np.random.RandomState(31)
+    x = torch.from_numpy(rng.randn(3, 32, 96, 96).astype(np.float32))     # >= 120 M tiles: the heuristic keeps one N tile
+    w0, w1, w2 = rand_conv(rng, 32, 64, 3), rand_conv(rng, 64, 32, 1), rand_conv(rng, 32, 64, 3)
+    sc = _lib.RtodLayerDesc()
+    sc.type, sc.src0, sc.src1 = _lib.LAYER_SHORTCUT, 2, 0
+    monkeypatch.setenv("RTOD_TC_FORCE", "0,0,1,1,2,0,2")      # bn 0 = by shape
+    cfgs = []
+    outs = run_block(lib, [conv_desc(64, 3, 1), conv_desc(32, 1, 1), conv_desc(64, 3, 1), sc], x, {0: w0, 1: w1, 2: w2}, configs=cfgs)
+    monkeypatch.delenv("RTOD_TC_FORCE")
+    assert [c["pipelines"] for c in cfgs] == [2, 2, 2] and [c["w_split"] for c in cfgs] == [1, 1, 1]
+    tol = BLOCK_TOL["fp16"]
+    assert frac_within(outs[0], ref_block(x, w0, 3, 1, True, "fp16", split=True), *tol) == 1.0
+    assert frac_within(outs[1], ref_block(outs[0], w1, 1, 1, True, "fp16", split=True), *tol) == 1.0
+    assert frac_within(outs[3], ref_block(outs[1], w2, 3, 1, True, "fp16", split=True) + outs[0], *tol) == 1.0
+
+
 def test_conv_block_two_term_weights_every_launch_configuration(lib, monkeypatch):
     monkeypatch.setenv("RTOD_WSPLIT_ELEMS", "0")
+    monkeypatch.setenv("RTOD_WSPLIT_AI", "10000")
     rng = np.random.RandomState(77)
     for cin, cout, k, stride, H, batch in [(64, 128, 3, 1, 52, 3), (32, 64, 3, 2, 104, 2), (256, 128, 1, 1, 52, 4)]:
         x = torch.from_numpy(rng.randn(batch, cin, H, H).astype(np.float32))
@@ -313,7 +372,9 @@ CONV_TC_PAIR, CONV_TC = 3, 2                # include/rtod.h RTOD_CONV_*
 
 # shapes large enough for the CTA-pair kernel (Cout % 256 == 0 and >= 60 pair tiles): an odd number of
 # 128-row tiles (the peer CTA of the last pair is entirely out of bounds), 1x1, stride 2, two N tiles
-PAIR_CASES = [(128, 256, 3, 1, 52, 6), (256, 512, 1, 1, 26, 12), (128, 256, 3, 2, 104, 6), (64, 512, 3, 1, 26, 11)]
+# ... and Cout = 128 / 384 (N tile 128: each CTA loads 64 weight rows)
+PAIR_CASES = [(128, 256, 3, 1, 52, 6), (256, 512, 1, 1, 26, 12), (128, 256, 3, 2, 104, 6), (64, 512, 3, 1, 26, 11),
+              (64, 128, 3, 1, 104, 2), (256, 128, 1, 1, 52, 6), (64, 128, 3, 2, 208, 2), (32, 384, 3, 1, 52, 3)]
 
 
 @pytest.mark.parametrize("cin,cout,k,stride,H,batch", PAIR_CASES)
@@ -331,6 +392,20 @@ def test_conv_block_cta_pair_kernel(lib, cin, cout, k, stride, H, batch, dtype, 
     assert got.shape == ref_q.shape
     assert frac_within(got, ref_q, *BLOCK_TOL[dtype]) == 1.0
 
+@pytest.mark.parametrize("cin,cout,k,stride,H,batch", [(256, 128, 1, 1, 52, 6), (64, 128, 3, 2, 208, 2), (64, 256, 3, 1, 52, 6)])
+def test_conv_block_cta_pair_kernel_two_term_weights(lib, monkeypatch, cin, cout, k, stride, H, batch):
+    monkeypatch.setenv("RTOD_WSPLIT_ELEMS", "0")
+    monkeypatch.setenv("RTOD_WSPLIT_AI", "10000")
+    rng = np.random.RandomState(cin + cout + k + stride + H + 1)
+    x = torch.from_numpy(rng.randn(batch, cin, H, H).astype(np.float32))
+    w = rand_conv(rng, cin, cout, k)
+    backends, splits = [], []
+    got = run_block(lib, [conv_desc(cout, k, stride)], x, {0: w}, _lib.PLAN_NO_AUTOTUNE, backends, splits)[0]
+    assert backends == [CONV_TC_PAIR] and splits == [1]
+    ref_q = ref_block(x, w, k, stride, True, "fp16", split=True)
+    assert frac_within(got, ref_q, *BLOCK_TOL["fp16"]) == 1.0
+
+
 @pytest.mark.parametrize("dtype,dflag", DTYPES)
 def test_residual_block_cta_pair_kernel(lib, dtype, dflag):
     """shortcut operand TMA-loaded in place by the per-warp epilogue, on the CTA-pair kernel"""
@@ -342,7 +417,7 @@ def test_residual_block_cta_pair_kernel(lib, dtype, dflag):
     backends = []
     outs = run_block(lib, [conv_desc(256, 3, 1), conv_desc(128, 1, 1), conv_desc(256, 3, 1), sc], x,
                      {0: w0, 1: w1, 2: w2}, _lib.PLAN_NO_AUTOTUNE | _lib.PLAN_NO_WSPLIT | dflag, backends)
-    assert backends[0] == CONV_TC_PAIR and backends[2] == CONV_TC_PAIR and backends[1] == CONV_TC
+    assert backends[0] == CONV_TC_PAIR and backends[2] == CONV_TC_PAIR and backends[1] in (CONV_TC, CONV_TC_PAIR)
     # every stage is checked against the reference evaluated on the DEVICE's own stored input of that stage
     tol = BLOCK_TOL[dtype]
     assert frac_within(outs[0], ref_block(x, w0, 3, 1, True, dtype), *tol) == 1.0
@@ -356,6 +431,8 @@ def test_residual_block_cta_pair_kernel(lib, dtype, dflag):
 # back to the default, which is covered anyway
 FORCED = ["0,%d,%d,%d,%d" % (bn, c, r, s) for bn in (256, 128, 64) for c in (1, 2, 3) for r in (0, 1) for s in (1, 2)]
 FORCED.append("1,256,1,0,2")
+# dual pipeline (two warp sets sharing resident weights): "pair,bn,ctas,resident,sbufs,split,pipelines"
+FORCED += ["0,%d,1,1,%d,0,2" % (bn, s) for bn in (128, 64, 32) for s in (1, 2)]
 
 
 @pytest.mark.parametrize("cin,cout,k,stride,H,batch", [(64, 128, 3, 1, 52, 3), (32, 64, 3, 2, 104, 2),

@@ -43,7 +43,9 @@ def test_prep_frames_against_oracle(h, w, dim):
         for b in range(3):
             assert torch.equal(got[b:b + 1].cpu(), prep_port.prep_image(frames[b], dim, resize=mode)), (b, mode)
     u8 = prep_frames(torch.from_numpy(frames), dim, resize=RESIZE_OPENCV, as_uint8=True)
-    assert u8.dtype == torch.uint8 and torch.equal(u8.float().div(255.0), prep_frames(torch.from_numpy(frames), dim, resize=RESIZE_OPENCV))
+    # (on the host: CUDA's div-by-scalar multiplies with the reciprocal, prep_image's is a true division)
+    assert u8.dtype == torch.uint8 and torch.equal(u8.cpu().float().div(255.0),
+                                                   prep_frames(torch.from_numpy(frames), dim, resize=RESIZE_OPENCV).cpu())
     assert letterbox_geometry(w, h, dim) == prep_port.letterbox_geometry(w, h, dim, dim)
     if h == w == dim:                                                  # same size: the resize is the identity
         assert torch.equal(u8.cpu(), torch.from_numpy(frames).flip(3).permute(0, 3, 1, 2))
