@@ -13,9 +13,10 @@ Darknet ``.weights`` file and ingested through ``load_weights`` like real ones.
 
 value   whole-job frames/s with the frames already resident in HBM (CUDA events, barrier + sync
         on both sides, max over ranks).
-e2e     the same metric through the public API with HOST buffers: pinned fp32 frames are copied
-        host->device inside the timed region (DetectionPipeline: side-stream copies overlap the
-        previous batch) and every step's detections are read back to the host.
+e2e     the same metric through the public API with HOST buffers: pinned uint8 BGR frames (what a camera or
+        cv2.imread delivers) are copied host->device inside the timed region (DetectionPipeline: side-stream
+        copies overlap the previous batch), letterboxed / scaled on the device, and every step's detections
+        are read back to the host.  e2e_fp32_frames: the same with fp32 [B,3,H,W] host tensors.
 roofline  the dominant kernel (conv_tc_kernel, tensor bound): sum of 2*M*N*K over its launches
         divided by the sum of their device times, measured per layer with CUDA events by
         rtod_plan_forward_profile inside this run; peak = MEASURED_PEAKS.json.
@@ -185,11 +186,57 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------ B200 arm
+def conv_traffic_record(workload_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the convolution launches of one forward, from the committed ncu
+    summary of this tree (profiles/r2_conv_traffic.json, produced by tools/ncu_traffic.sh) -- None if there is none
+    for this workload."""
+    path = os.path.join(ROOT, "profiles", "r2_conv_traffic.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        with open(path) as fh:
+            rec = json.load(fh)
+        return rec.get(workload_key)
+    except (OSError, ValueError):
+        return None
+
+
+def synth_microbench_tensor(dev, density, clustered, seed=7, B=256, N=10647, C=80):
+    """BASELINE configs[3] tensor generated on the device: `density` of the rows of every image
+    above objectness 0.5; clustered = the hot rows are jittered copies of 12 objects per image with a dominant class,
+    so that NMS actually suppresses."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    mb = torch.rand(B, N, 5 + C, device=dev, generator=g)
+    mb[..., 0:2] *= RESO
+    mb[..., 2:4] = torch.exp(mb[..., 2:4] * 3 + 2)
+    hot = torch.rand(B, N, device=dev, generator=g) < density
+    mb[..., 4] = torch.where(hot, 0.5 + 0.4995 * mb[..., 4], 0.4995 * mb[..., 4])
+    if clustered:
+        n_obj = 12
+        centres = torch.rand(B, n_obj, 2, device=dev, generator=g) * (RESO - 80) + 40
+        sizes = torch.exp(torch.rand(B, n_obj, 2, device=dev, generator=g) * 2 + 3)
+        classes = torch.randint(0, C, (B, n_obj), device=dev, generator=g)
+        which = torch.randint(0, n_obj, (B, N), device=dev, generator=g)
+        bi = torch.arange(B, device=dev).unsqueeze(1).expand(B, N)
+        ctr = centres[bi, which] + torch.randn(B, N, 2, device=dev, generator=g) * 0.15 * sizes[bi, which]
+        wh = sizes[bi, which] * torch.exp(torch.randn(B, N, 2, device=dev, generator=g) * 0.15)
+        h3 = hot.unsqueeze(2)
+        mb[..., 0:2] = torch.where(h3, ctr, mb[..., 0:2])
+        mb[..., 2:4] = torch.where(h3, wh, mb[..., 2:4])
+        mb[..., 5:] = torch.where(h3, mb[..., 5:] * 0.5, mb[..., 5:])
+        dom = torch.rand(B, N, device=dev, generator=g) * 0.4 + 0.6
+        cls_idx = classes[bi, which]
+        cur = mb[..., 5:].gather(2, cls_idx.unsqueeze(2)).squeeze(2)
+        mb[..., 5:].scatter_(2, cls_idx.unsqueeze(2), torch.where(hot, dom, cur).unsqueeze(2))
+    return mb
+
+
 def run_b200(args):
     import torch.distributed as dist
     from realtimeobjectdetection_b200 import Darknet, _lib, write_results, write_results_async
     from realtimeobjectdetection_b200.pipeline import DetectionPipeline
-    from realtimeobjectdetection_b200.sharding import gather_detections
+    from realtimeobjectdetection_b200.sharding import gather_detections_async
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -211,6 +258,7 @@ def run_b200(args):
     model.eval()
     model.borrow_output = True                    # predictions are consumed in-stream: no copies around the CUDA graph
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    cap_rows = 256 * B                            # fixed capacity of the per-step detection gather (rows per rank)
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -221,65 +269,72 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    pending = [None]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def collect():
-        """detections of the step enqueued before the current one (None at the first step)"""
-        if pending[0] is None:
-            return None
-        det = pending[0].result()
-        pending[0] = None
+    def max_over_ranks(ms_local):
+        ms = torch.tensor([ms_local], device=dev)
         if world > 1:
-            det = gather_detections(det, rank * B)       # rows to rank 0 (NCCL), img index made global
-        return det
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
 
-    def step(i):
-        # streaming: step i is enqueued before step i-1's detection count is awaited, so the GPU never idles
-        # on the host; every step's detections are collected inside the timed region (flush after the loop)
-        pred = model(frames[i & 1])
-        handle = write_results_async(pred, CLASSES, CONF, NMS)
-        det = collect()
-        pending[0] = handle
-        return det
+    def streaming_loop(net, batches, n_warm, n_steps, first_frame, capacity):
+        """forward + write_results over resident frame batches, detections collected one step late (the GPU never
+        idles on the host); at N > 1 every step's rows go to rank 0 through ONE fixed-capacity NCCL gather on a side
+        stream.  Returns (ms of the n_steps timed steps on this rank, detections seen on rank 0, wall t0, t1)."""
+        pending = [None]
 
-    n_det = 0
-    for i in range(W):
-        step(i)
-    collect()
-    barrier()
+        def collect():
+            if pending[0] is None:
+                return None
+            det = pending[0].result()
+            pending[0] = None
+            return det
+
+        def step(i):
+            pred = net(batches[i & 1])
+            handle = write_results_async(pred, CLASSES, CONF, NMS)
+            if world > 1:
+                handle = gather_detections_async(handle.rows_device, handle.count_device, first_frame, capacity)
+            det = collect()
+            pending[0] = handle
+            return det
+
+        for i in range(n_warm):
+            step(i)
+        collect()
+        barrier()
+        n_seen = 0
+        t0 = time.time()
+        e0.record()
+        for i in range(n_steps + 1):
+            det = step(i) if i < n_steps else collect()      # n_steps enqueued, n_steps results collected
+            if det is not None and not isinstance(det, int):
+                n_seen += det.size(0)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), n_seen, t0, time.time()
+
+    # ---- value: frames resident in HBM --------------------------------------------------------------------
+    streaming_loop(model, frames, W, 0, rank * B, cap_rows)          # binds + autotunes + captures the graphs
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.25)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0 = time.time()
-    e0.record()
-    for i in range(K + 1):
-        det = step(i) if i < K else collect()            # K steps enqueued, K results collected
-        if rank == 0 and not isinstance(det, int) and det is not None:
-            n_det += det.size(0)
-    e1.record()
-    barrier()
-    t1 = time.time()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_local, n_det, t0, t1 = streaming_loop(model, frames, 1, K, rank * B, cap_rows)
+    ms_total = max_over_ranks(ms_local)
     clocks = sampler.stop(t0, t1)
     value = world * B * K / (ms_total / 1e3)
     model.check_device()
+    plan = next(p for p in model._plans.values() if p.key[0] == B and p.key[2] == RESO)
     # nvidia-smi gets only a handful of samples inside a ~0.1 s timed region: a second, UNTIMED pass of the same
     # steps with a one-thread kernel counting SM cycles per 0.5 ms of wall time on a side stream
     # (rtod_sm_clock_probe; it slows the step down, which is why it is not part of the timed region)
     try:
         side = torch.cuda.Stream(dev)
-        n_win = max(8, int(K * (ms_total / K) / 0.5))
+        n_win = max(8, int(ms_total / 0.5))
         mhz = torch.zeros(n_win, device=dev)
         torch.cuda.synchronize()
         _lib.check(lib.rtod_sm_clock_probe(mhz.data_ptr(), n_win, 500, side.cuda_stream))
-        for i in range(K + 2):
-            step(i)
-        collect()
+        streaming_loop(model, frames, 0, K + 2, rank * B, cap_rows)
         torch.cuda.synchronize()
         vals = sorted(float(v) for v in mhz.cpu() if v > 0)
         if vals:
@@ -288,50 +343,61 @@ def run_b200(args):
     except Exception as exc:                      # measurement aid only
         clocks["sm_mhz_in_kernel"] = {"error": str(exc)}
 
-    # ---- e2e: host buffers, H2D inside the timed region, detections read back ------------------
-    host = [torch.rand(B, 3, RESO, RESO).pin_memory() for _ in range(2)]
-    pipe = DetectionPipeline(model, CLASSES, CONF, NMS, device=dev)
-    for _ in pipe.run(host[i & 1] for i in range(W)):
-        pass
-    pipe.h2d_bytes = pipe.d2h_bytes = 0
-    barrier()
-    e0.record()
-    for det in pipe.run(host[i & 1] for i in range(K)):
-        if world > 1:
-            gather_detections(det if isinstance(det, int) else det.to(dev), rank * B)
-    e1.record()
-    barrier()
-    ms_e = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * K / (float(ms_e.item()) / 1e3)
-    e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes // K,
-           "d2h_bytes_per_step": pipe.d2h_bytes // K, "ms_per_step": float(ms_e.item()) / K,
-           "api": "DetectionPipeline(model).run(pinned host batches) -> Darknet.forward + write_results -> .cpu()"}
+    # ---- e2e: HOST buffers through the public API ----------------------------------------------------------
+    # uint8 BGR frames at network resolution in pinned host memory (what a camera / video decoder delivers, the
+    # reference feeds cv2.imread output to prep_image): H2D of the raw bytes on a side stream, letterbox + BGR->RGB +
+    # /255 on the device (rtod_prep_image), forward, write_results, detections read back to the host every step
+    def e2e_run(host_batches, tag):
+        gather = {"first_frame": rank * B, "capacity": cap_rows} if world > 1 else None
+        pipe = DetectionPipeline(model, CLASSES, CONF, NMS, device=dev, gather=gather)
+        for _ in pipe.run(host_batches[i & 1] for i in range(W)):
+            pass
+        pipe.h2d_bytes = pipe.d2h_bytes = 0
+        barrier()
+        e0.record()
+        for _ in pipe.run(host_batches[i & 1] for i in range(K)):
+            pass
+        e1.record()
+        barrier()
+        ms_e = max_over_ranks(e0.elapsed_time(e1))
+        return {"value": world * B * K / (ms_e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes // K,
+                "d2h_bytes_per_step": pipe.d2h_bytes // K, "ms_per_step": ms_e / K, "api": tag}
+
+    rng = np.random.RandomState(99 + rank)
+    host_u8 = [torch.from_numpy(rng.randint(0, 256, (B, RESO, RESO, 3), dtype=np.uint8)).pin_memory() for _ in range(2)]
+    e2e = e2e_run(host_u8, "DetectionPipeline(model).run(pinned uint8 [B,%d,%d,3] BGR host frames) -> rtod_prep_image -> "
+                           "Darknet.forward -> write_results -> host rows" % (RESO, RESO))
+    host_f32 = [torch.rand(B, 3, RESO, RESO).pin_memory() for _ in range(2)]
+    e2e_f32 = e2e_run(host_f32, "same pipeline fed pinned fp32 [B,3,%d,%d] host tensors (what prep_image returns)" % (RESO, RESO))
+    del host_u8, host_f32
 
     # ---- roofline of the dominant kernel, measured live per layer --------------------------------
     peaks = measured_peaks()
-    plan = next(reversed(model._plans.values()))
     n_layers = len(blocks) - 1
     ms_arr = (ctypes.c_float * (n_layers + 1))()
     kind_arr = (ctypes.c_int * n_layers)()
     pred_buf = torch.empty(B, plan.n_rows, plan.n_attrs, device=dev)
-    tc_ms, tc_flops, per_layer = 0.0, 0.0, []
+    tc_ms, tc_flops, per_layer, decode_ms = 0.0, 0.0, [], 0.0
     reps = 3
     for r in range(reps + 1):
         _lib.check(lib.rtod_plan_forward_profile(plan.handle, frames[r & 1].data_ptr(), pred_buf.data_ptr(), 0,
                                                  torch.cuda.current_stream(dev).cuda_stream, ms_arr, kind_arr))
         if r == 0:
             continue                                   # warm-up pass of the profiled (non-graph) path
+        decode_ms += ms_arr[n_layers] / reps
         for i in range(n_layers):
             if kind_arr[i] == 1:
                 tc_ms += ms_arr[i]
                 tc_flops += lib.rtod_plan_layer_flops(plan.handle, i)
-    fwd_ms = sum(ms_arr[i] for i in range(n_layers + 1))
+    cfg12 = (ctypes.c_int * 12)()
     for i in range(n_layers):
         if kind_arr[i]:
-            per_layer.append((i, int(kind_arr[i]), round(float(ms_arr[i]), 4),
-                              round(lib.rtod_plan_layer_flops(plan.handle, i) / max(ms_arr[i], 1e-6) / 1e9, 1)))
+            row = [i, int(kind_arr[i]), round(float(ms_arr[i]), 4),
+                   round(lib.rtod_plan_layer_flops(plan.handle, i) / max(ms_arr[i], 1e-6) / 1e9, 1)]
+            if kind_arr[i] == 1 and lib.rtod_plan_conv_config(plan.handle, i, cfg12) == 0:
+                row.append({"pair": int(cfg12[0] == 3), "bn": cfg12[1], "ctas": cfg12[2], "resident": cfg12[3],
+                            "pipelines": cfg12[8], "stages": cfg12[9], "two_term_weights": cfg12[10]})
+            per_layer.append(row)
     n_tc = sum(1 for i in range(n_layers) if kind_arr[i] == 1)
     # the figure that is reported: CUDA events only where the stream switches between the tcgen05 convolution
     # launches and the other kernels (an event after each of the 74 launches adds a 2-5 us gap to every one)
@@ -346,23 +412,29 @@ def run_b200(args):
             seg_other += other_ms_c.value / seg_reps
     per_launch_achieved = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
     achieved = (tc_flops / reps) / (seg_conv / 1e3) / 1e12 if seg_conv > 0 else 0.0
-    tc_ms = seg_conv * reps
     fwd_ms = seg_conv + seg_other
-    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel + conv_pair_kernel", "achieved": achieved,
-                "achieved_with_per_launch_events": per_launch_achieved,
-                "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tflops_sustained"],
-                # dram__bytes_read + dram__bytes_write of one captured conv_pair_kernel launch (13x13 3x3 512->1024
-                # layer at B=64, ncu --set full: 42.70 MB read + 1.33 MB written before the kernel ends; the output
-                # stays in L2); its algorithmic bytes (in + weights + out, bf16) are 42.6 MB
-                "traffic": 44.0e6 if (args.cfg == "yolov3" and B == 64 and RESO == 416) else None,
+    workload_key = "%s-%d-B%d-%s" % (args.cfg, RESO, B, "fp16" if plan.is_f16 else "bf16")
+    traffic = conv_traffic_record(workload_key)
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel + conv_pair_kernel (the %d tcgen05 convolution launches of a forward)" % n_tc,
+                "achieved": achieved, "achieved_with_per_launch_events": per_launch_achieved,
+                "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
+                "frac_of_burst_peak": achieved / peaks["tflops_burst"],
+                # dram bytes per launch (mean over the launches of one forward) from the committed ncu pass, else null
+                "traffic": (traffic["dram_bytes_per_launch"] if traffic else None),
+                "traffic_source": (traffic.get("source") if traffic else None),
+                "algorithmic_bytes_per_launch": (traffic.get("algorithmic_bytes_per_launch") if traffic else None),
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s): kernel timed inside a long step"
                                % peaks["source"],
                 "launches_per_step": n_tc, "flops_per_step": tc_flops / reps,
-                "avg_launch_ms": tc_ms / reps / max(n_tc, 1), "share_of_forward": tc_ms / reps / fwd_ms}
+                "avg_launch_ms": seg_conv / max(n_tc, 1), "share_of_forward": seg_conv / fwd_ms}
+    dec_bytes = B * plan.n_rows * plan.n_attrs * 8            # fp32 logits in, fp32 prediction out
+    roofline_decode = {"bound": "hbm", "kernel": "yolo_decode_heads_fast_kernel (one launch, all heads)", "ms": decode_ms,
+                       "achieved": dec_bytes / max(decode_ms, 1e-9) / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": dec_bytes / max(decode_ms, 1e-9) / 1e6 / peaks["hbm_gbs"], "traffic": None,
+                       "bytes_per_launch": dec_bytes}
 
     # NMS stage (HBM bound): device time of the rtod_write_results C-ABI call (scan + image x2 + emit
-    # kernels) on this step's prediction tensor, and on the BASELINE configs[3] microbench tensor
+    # kernels) on this step's prediction tensor, and on the BASELINE configs[3] microbench tensors
     def time_write_results(pred_t, iters=10):
         Bq, Nq, Lq = pred_t.shape
         nbytes = lib.rtod_write_results_workspace_bytes(Bq, Nq, Lq - 5)
@@ -381,7 +453,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters, int(cnt.item())
 
-    pred = model(frames[0])
+    pred = model(frames[0]).clone()
     nms_ms, _ = time_write_results(pred)
     nms_bytes = pred.numel() * 4
     roofline_nms = {"bound": "hbm", "kernel": "rtod_write_results: nms_scan + nms_image(light, heavy) + nms_emit",
@@ -390,23 +462,36 @@ def run_b200(args):
                     "tensor": list(pred.shape)}
     microbench = None
     if rank == 0 and not args.no_latency:
-        # BASELINE configs[3]: [256, 10647, 85], 1 % of the rows above the threshold, generated on device
-        g2 = torch.Generator(device=dev)
-        g2.manual_seed(7)
-        mb = torch.rand(256, 10647, 85, device=dev, generator=g2)
-        mb[..., 0:2] *= RESO
-        mb[..., 2:4] = torch.exp(mb[..., 2:4] * 3 + 2)
-        hot = torch.rand(256, 10647, device=dev, generator=g2) < 0.01
-        mb[..., 4] = torch.where(hot, 0.5 + 0.4995 * mb[..., 4], 0.4995 * mb[..., 4])
-        mb_ms, mb_det = time_write_results(mb)
-        microbench = {"what": "write_results on [256,10647,85] fp32, 1% of rows above conf 0.5 (uniform boxes)",
-                      "ms": mb_ms, "GB/s": mb.numel() * 4 / mb_ms / 1e6,
-                      "frac_of_hbm_peak": mb.numel() * 4 / mb_ms / 1e6 / peaks["hbm_gbs"], "detections": mb_det}
-        del mb, hot
+        microbench = []
+        for density, clustered in ((0.01, False), (0.01, True), (0.10, True), (0.50, True)):
+            mb = synth_microbench_tensor(dev, density, clustered)
+            mb_ms, mb_det = time_write_results(mb)
+            microbench.append({"what": "write_results on [256,10647,85] fp32, %.0f %% of rows above conf 0.5, %s boxes"
+                                       % (100 * density, "clustered" if clustered else "uniform"),
+                               "ms": mb_ms, "GB/s": mb.numel() * 4 / mb_ms / 1e6,
+                               "frac_of_hbm_peak": mb.numel() * 4 / mb_ms / 1e6 / peaks["hbm_gbs"], "detections": mb_det})
+            del mb
+        g3 = torch.Generator(device=dev)
+        g3.manual_seed(11)
+        heads = torch.randn(256, 255, 52, 52, device=dev, generator=g3)
+        from realtimeobjectdetection_b200 import predict_transform
+        for _ in range(3):
+            predict_transform(heads, RESO, [(10, 13), (16, 30), (33, 23)], 80, True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            predict_transform(heads, RESO, [(10, 13), (16, 30), (33, 23)], 80, True)
+        e1.record()
+        torch.cuda.synchronize()
+        d_ms = e0.elapsed_time(e1) / 10
+        microbench.append({"what": "predict_transform (rtod_yolo_decode) on randn [256,255,52,52] fp32 NCHW", "ms": d_ms,
+                           "GB/s": heads.numel() * 8 / d_ms / 1e6, "frac_of_hbm_peak": heads.numel() * 8 / d_ms / 1e6 / peaks["hbm_gbs"]})
+        del heads
 
     # ---- p50 batch-1 latency (BASELINE configs[1]) ---------------------------------------------------
     latency = None
     if not args.no_latency and rank == 0:
+        model.borrow_output = False
         x1 = torch.rand(1, 3, RESO, RESO, device=dev)
         for _ in range(20):
             write_results(model(x1), CLASSES, CONF, NMS)
@@ -418,7 +503,70 @@ def run_b200(args):
             e1.synchronize()
             lat.append(e0.elapsed_time(e1))
         latency = {"p50_ms": statistics.median(lat), "p99_ms": sorted(lat)[197], "batch": 1,
-                   "what": "Darknet.forward + write_results, frame resident in HBM, CUDA events"}
+                   "what": "Darknet.forward + write_results (reference call semantics: fresh tensors, synchronous result), "
+                           "frame resident in HBM, CUDA events"}
+        model.borrow_output = True
+
+    # ---- BASELINE configs[2]: YOLOv3 608x608, GLOBAL batch 64 sharded over the ranks (strong scaling) -------
+    config2 = None
+    if not args.no_latency and args.cfg == "yolov3" and RESO == 416 and 64 % world == 0:
+        b2 = 64 // world
+        model.net_info["height"] = 608
+        g2 = torch.Generator(device=dev)
+        g2.manual_seed(4321 + rank)
+        big = [torch.rand(b2, 3, 608, 608, device=dev, generator=g2) for _ in range(2)]
+        k2 = max(4, K // 2)
+        streaming_loop(model, big, 3, 0, rank * b2, 256 * b2)
+        ms2, _, _, _ = streaming_loop(model, big, 1, k2, rank * b2, 256 * b2)
+        ms2 = max_over_ranks(ms2)
+        config2 = {"workload": "yolov3.cfg 608x608 forward+decode+NMS, global batch 64 = %d frames per GPU x %d GPUs, "
+                               "detections gathered to rank 0" % (b2, world),
+                   "value": 64 * k2 / (ms2 / 1e3), "unit": "frames/s", "ms_per_step": ms2 / k2, "steps": k2, "scaling": "strong",
+                   "forward_tflops": 140.692 * 64 / (ms2 / k2)}
+        model.net_info["height"] = RESO
+        del big
+
+    # ---- BASELINE configs[4]: YOLOv3-tiny 320x320 streaming, batch 1, uint8 frames, pinned async H2D --------------
+    config4 = None
+    if not args.no_latency and rank == 0:
+        from realtimeobjectdetection_b200.cfg import builtin_cfg
+        tcfg, tblocks, tstream, tpath = synthetic_weights_file("yolov3-tiny")
+        tiny = Darknet(builtin_cfg("yolov3-tiny"), True)
+        tiny.load_weights(tpath)
+        os.remove(tpath)
+        tiny.net_info["height"] = 320
+        tiny.eval()
+        rng4 = np.random.RandomState(5)
+        vid = [torch.from_numpy(rng4.randint(0, 256, (1, 320, 320, 3), dtype=np.uint8)).pin_memory() for _ in range(8)]
+        pipe4 = DetectionPipeline(tiny, CLASSES, CONF, NMS, device=dev, collect_lag=0)
+        for _ in pipe4.run(vid[i & 7] for i in range(50)):
+            pass
+        lat4 = []
+        it4 = pipe4.run(vid[i & 7] for i in range(1000))
+        torch.cuda.synchronize()
+        t_all = time.perf_counter()
+        while True:
+            t = time.perf_counter()
+            try:
+                next(it4)
+            except StopIteration:
+                break
+            lat4.append((time.perf_counter() - t) * 1e3)
+        t_all = time.perf_counter() - t_all
+        lat4.sort()
+        pipe5 = DetectionPipeline(tiny, CLASSES, CONF, NMS, device=dev, collect_lag=1)
+        torch.cuda.synchronize()
+        t5 = time.perf_counter()
+        for _ in pipe5.run(vid[i & 7] for i in range(1000)):
+            pass
+        t5 = time.perf_counter() - t5
+        config4 = {"workload": "yolov3-tiny.cfg 320x320 streaming, batch 1, 1000 uint8 [1,320,320,3] frames in pinned host "
+                               "memory, async H2D on a side stream, device letterbox, detections to the host",
+                   "latency_ms_p50": lat4[len(lat4) // 2], "latency_ms_p99": lat4[int(len(lat4) * 0.99)],
+                   "frames_per_s_latency_mode": len(lat4) / t_all, "frames_per_s_throughput_mode": 1000 / t5,
+                   "how": "host wall clock per frame: H2D enqueue -> detections on the host (collect_lag=0); "
+                          "throughput mode collects one frame late"}
+        del tiny
 
     # ---- CPU baseline (rank 0, N=1 only; bounded sample) ------------------------------------------
     cpu = None
@@ -429,7 +577,7 @@ def run_b200(args):
                          % sum(times)}
 
     if rank == 0:
-        launches_per_step = plan.launches + 3 + (1 if world > 1 else 0)
+        launches_per_step = plan.launches + 4      # forward (convs, upsample, decode) + nms scan / image x2 / emit
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -437,16 +585,21 @@ def run_b200(args):
             "config": {"workload": "yolov3.cfg %dx%d forward+decode+NMS, 80 classes, conf 0.5 / nms 0.4, " % (RESO, RESO) +
                                    "batch %d per GPU" % B,
                        "global_batch": world * B, "parallelism": "frames sharded, dp%d, no collective on the hot "
-                                                                 "path; detections gathered to rank 0" % world,
+                                                                 "path; detections gathered to rank 0 by one "
+                                                                 "fixed-capacity NCCL gather per step on a side stream" % world,
                        "weights": "synthetic calibrated seed 0 via load_weights", "bn": "folded (eval)",
+                       "storage": "fp16 activations/weights, fp32 accumulate, two-term fp16 weights in the memory-bound layers"
+                                  if plan.is_f16 else "bf16 activations/weights, fp32 accumulate",
                        "l2": "inputs alternate between two %.0f MB frame batches and every step streams >1 GB of "
                              "activations (> 126 MB L2)" % (B * 3 * RESO * RESO * 4 / 1e6),
                        "detections_per_step": n_det / max(K, 1), "cuda_graph": bool(model.use_cuda_graph)},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K,
+            "clocks": clocks, "e2e": e2e, "e2e_fp32_frames": e2e_f32, "gpu_launches": launches_per_step * K,
             "gpu_launches_per_step": launches_per_step,
-            "roofline": roofline, "roofline_nms": roofline_nms, "nms_microbench": microbench,
-            "forward_tflops": FRAME_GFLOP * world * B / (ms_total / K) if args.cfg == "yolov3" else None,
-            "latency_batch1": latency, "cpu_baseline": cpu, "layers": per_layer,
+            "roofline": roofline, "roofline_decode": roofline_decode, "roofline_nms": roofline_nms,
+            "nms_microbench": microbench,
+            "forward_tflops": FRAME_GFLOP * world * B / (ms_total / K) if args.cfg == "yolov3" and RESO == 416 else None,
+            "latency_batch1": latency, "config2_608_batch64": config2, "config4_tiny320_streaming": config4,
+            "cpu_baseline": cpu, "layers": per_layer,
         }
         print(json.dumps(line))
     if world > 1:

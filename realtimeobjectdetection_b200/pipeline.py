@@ -20,7 +20,7 @@ from .util import prep_frames, write_results_async
 
 class DetectionPipeline:
     def __init__(self, model, num_class: int, confidence: float = 0.6, nms_conf: float = 0.4,
-                 device=None, depth: int = 2, collect_lag: int = 1, resize: int = 0):
+                 device=None, depth: int = 2, collect_lag: int = 1, resize: int = 0, gather: dict = None):
         if not torch.cuda.is_available():
             raise RuntimeError("DetectionPipeline needs a CUDA device; there is no CPU fallback")
         self.model, self.num_class = model, int(num_class)
@@ -32,6 +32,11 @@ class DetectionPipeline:
         # is requested from the source.
         self.collect_lag = 1 if collect_lag else 0
         self.resize = int(resize)                              # util.RESIZE_FLOAT / RESIZE_OPENCV for uint8 frames
+        # multi-GPU (one process per GPU, frames sharded): {"first_frame": global index of this rank's frame 0 in a
+        # batch, "capacity": rows per rank and step, "group": None, "dst": 0} -> every batch's detections are gathered
+        # to `dst` with one fixed-capacity collective on a side stream (sharding.gather_detections_async); run() then
+        # yields the global rows on `dst` and None on the other ranks
+        self.gather = gather
         self.copy_stream = torch.cuda.Stream(self.device)
         self._slots = []
         self.h2d_bytes = 0
@@ -95,6 +100,11 @@ class DetectionPipeline:
                 pred = self.model(self._network_input(pending))
                 handle = write_results_async(pred, self.num_class, self.confidence, self.nms_conf)
                 pending["free"].record(compute)
+                if self.gather is not None:
+                    from .sharding import gather_detections_async
+                    g = self.gather
+                    handle = gather_detections_async(handle.rows_device, handle.count_device, g["first_frame"],
+                                                     g["capacity"], g.get("group"), g.get("dst", 0))
                 if self.collect_lag == 0:
                     yield self._collect(handle)
                 else:
@@ -109,6 +119,11 @@ class DetectionPipeline:
             self.model.borrow_output = borrow
 
     def _collect(self, handle):
+        if self.gather is not None:
+            det = handle.result()                              # PendingGather: host rows on dst, None elsewhere
+            if det is not None:
+                self.d2h_bytes += handle.bucket_bytes
+            return det
         det = handle.result(to_host=True)
         if not isinstance(det, int):
             self.d2h_bytes += det.numel() * 4

@@ -61,6 +61,7 @@ class PendingGather:
     def __init__(self, rank, dst, world, capacity, bucket_host, done, work):
         self._rank, self._dst, self._world, self._cap = rank, dst, world, capacity
         self._bucket_host, self._done, self._work = bucket_host, done, work
+        self.bucket_bytes = 0 if bucket_host is None else bucket_host.numel() * 4      # device -> host bytes on dst
 
     def result(self):
         """On ``dst``: the concatenated ``[D, 8]`` rows (image index global) or 0; elsewhere None.  Waits only for

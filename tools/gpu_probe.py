@@ -235,7 +235,7 @@ def stage_ncufwd():
     """one stream-launched forward + write_results between cudaProfilerStart/Stop (ncu --profile-from-start off):
     the plan is bound (and autotuned) and warmed up outside the profiled range"""
     lib = _lib.load()
-    cfg, blocks, stream, state = make_network("yolov3", 3, "calibrated")
+    cfg, blocks, stream, state = make_network("yolov3", 0, "calibrated")      # bench.py's weights
     batch = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     model = Darknet(cfg, True)
     model.load_state_dict({**model.state_dict(), **state})

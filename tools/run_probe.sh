@@ -1,7 +1,6 @@
-(cd tools && timeout 120 ./umma_shift64_probe > ../gpurun_out/r2e_shift64.log 2>&1)
-timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | grep -E "^FAILED|^ERROR|passed|failed|^E  " | head -40 > gpurun_out/r2e_pytest.log
-echo "== default" > gpurun_out/r2e_probe.log
-RTOD_TC_TUNE_DBG=1 timeout 300 python tools/layer_probe.py L1 L2 L3 L5 L6 L7 L13 L99 >> gpurun_out/r2e_probe.log 2>&1
-echo "== no split" >> gpurun_out/r2e_probe.log
-RTOD_WSPLIT_AI=0 RTOD_TC_TUNE_DBG=1 timeout 300 python tools/layer_probe.py L1 L2 L3 L6 >> gpurun_out/r2e_probe.log 2>&1
-cat gpurun_out/r2e_pytest.log
+echo "== tc kernel heuristic config, trace stamps" > gpurun_out/r2h_probe.log
+for L in L13 L38 L63 L64; do
+RTOD_TC_NO_PAIR=1 PROBE_FLAGS=4 RTOD_LIB=$PWD/realtimeobjectdetection_b200/librtod_trace.so RTOD_CLK_DBG=1 PROBE_REPS=2 timeout 120 python tools/layer_probe.py $L 2>&1 | tail -6 >> gpurun_out/r2h_probe.log
+done
+echo "== same, no trace" >> gpurun_out/r2h_probe.log
+RTOD_TC_NO_PAIR=1 PROBE_FLAGS=4 timeout 120 python tools/layer_probe.py L13 L38 L63 L64 >> gpurun_out/r2h_probe.log 2>&1
