@@ -115,6 +115,12 @@ int rtod_plan_set_conv_weights(RtodPlan* plan, int layer, const float* weight, c
  * yolo layer. */
 int rtod_plan_forward(RtodPlan* plan, const float* x_nchw, float* pred, int train, void* stream);
 
+/* Same forward for uint8 frames: x_planes is [batch, 3, in_h, in_w] uint8 (what rtod_prep_image writes with
+ * out_u8), interpreted as value / 255 like prep_image (src/util.py:396) -- the scale is folded into the stem's
+ * weights, the pixels enter the tensor cores exactly.  fp16 storage plans whose first layer is a 3x3 / stride-1
+ * convolution of 16 / 32 / 64 filters over 3 channels (both reference networks); RTOD_ERR_UNSUPPORTED otherwise. */
+int rtod_plan_forward_u8(RtodPlan* plan, const unsigned char* x_planes, float* pred, int train, void* stream);
+
 /* Measurement: same as rtod_plan_forward, but brackets every layer with CUDA events on `stream`,
  * synchronises, and returns the device time of each layer's launch in layer_ms_host[0..n_layers)
  * and of the decode launch in layer_ms_host[n_layers] (HOST arrays; layer_kind_host may be null:

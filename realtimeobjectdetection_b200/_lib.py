@@ -61,6 +61,7 @@ _PROTOTYPES = {
     "rtod_plan_bind": (_i, [_vp, _vp, _sz, _vp, _sz]),
     "rtod_plan_set_conv_weights": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp]),
     "rtod_plan_forward": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "rtod_plan_forward_u8": (_i, [_vp, _vp, _vp, _i, _vp]),
     "rtod_plan_forward_profile": (_i, [_vp, _vp, _vp, _i, _vp, ctypes.POINTER(_f), ctypes.POINTER(_i)]),
     "rtod_plan_forward_segments": (_i, [_vp, _vp, _vp, _i, _vp, ctypes.POINTER(_f), ctypes.POINTER(_f)]),
     "rtod_plan_layer_flops": (ctypes.c_double, [_vp, _i]),

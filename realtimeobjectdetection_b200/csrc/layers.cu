@@ -412,7 +412,12 @@ int launch_stem_conv(const float* x, int B, int Cin, int H, int W, const float* 
                      int Cout, int ks, int stride, int pad, int leaky, Act out, cudaStream_t stream) {
     if (Cin != 3 || ks != 3 || Cout % 8 != 0 || Cout > 256 || out.fp32)
         return fail(RTOD_ERR_UNSUPPORTED, "stem conv supports 3x3, Cin=3, Cout%%8==0, Cout<=256");
-    // stride-1 stems (both reference networks): TMA-staged strips, see stem.cu
+    // fp16 storage, stride-1 stems of 16/32/64 filters (both reference networks): tcgen05 with the im2col operand
+    // built in shared memory, see stem_tc.cu
+    if (getenv("RTOD_STEM_NO_TC") == nullptr && out.f16 && stride == 1 && pad == 1 && W % 4 == 0 && W >= 160 &&
+        (Cout == 16 || Cout == 32 || Cout == 64) && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && out.H == H && out.W == W)
+        return launch_stem_tc(x, nullptr, B, H, W, w, bias, Cout, leaky, out, stream);
+    // stride-1 stems, bf16 storage: TMA-staged strips + warp-level MMA, see stem.cu
     if (getenv("RTOD_STEM_NO_TMA") == nullptr && stride == 1 && pad == 1 && W % 4 == 0 && W >= 64 && (Cout == 16 || Cout == 32 || Cout == 64) &&
         (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && out.H == H && out.W == W)
         return launch_stem_tma(x, B, H, W, w, bias, Cout, leaky, out, stream);

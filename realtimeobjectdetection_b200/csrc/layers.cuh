@@ -35,6 +35,9 @@ int launch_stem_conv(const float* x_nchw, int B, int Cin, int H, int W, const fl
                      cudaStream_t stream);
 int launch_stem_tma(const float* x_nchw, int B, int H, int W, const float* w_f32, const float* bias, int Cout,
                     int leaky, Act out, cudaStream_t stream);   // stem.cu
+// stem_tc.cu: tcgen05 stem for fp16 storage; fp32 NCHW frames or uint8 planes (value / 255 folded into the weights)
+int launch_stem_tc(const float* x_f32, const unsigned char* x_u8, int B, int H, int W, const float* w_f32, const float* bias,
+                   int Cout, int leaky, Act out, cudaStream_t stream);
 int launch_nchw_to_nhwc(const float* x_nchw, int B, Act out, cudaStream_t stream);
 int launch_nhwc_to_nchw(Act in, int B, float* out_nchw, cudaStream_t stream);
 int launch_maxpool(Act in, Act out, int B, int size, int stride, cudaStream_t stream);

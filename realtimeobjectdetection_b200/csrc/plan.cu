@@ -566,9 +566,11 @@ static int mark_segment(Segments* seg, int cls, cudaStream_t stream) {
 }
 
 static int run_forward(RtodPlan* p, const float* x, float* pred, int train, cudaStream_t stream,
-                       cudaEvent_t* ev, Segments* seg = nullptr) {
+                       cudaEvent_t* ev, Segments* seg = nullptr, const unsigned char* x_u8 = nullptr) {
     if (!p || !p->bound) return fail(RTOD_ERR_STATE, "rtod_plan_forward: plan is not bound");
-    if (!x) return fail(RTOD_ERR_BAD_ARG, "rtod_plan_forward: input is null");
+    if (!x && !x_u8) return fail(RTOD_ERR_BAD_ARG, "rtod_plan_forward: input is null");
+    if (x_u8 && !(p->nodes.size() && p->nodes[0].stem && p->f16 && p->nodes[0].d.stride == 1 && p->nodes[0].d.pad == 1))
+        return fail(RTOD_ERR_UNSUPPORTED, "rtod_plan_forward_u8: needs fp16 storage and a 3x3 / stride 1 stem convolution");
     if (p->heads.count && !pred) return fail(RTOD_ERR_BAD_ARG, "rtod_plan_forward: pred is null");
     const int n = (int)p->nodes.size();
     for (int i = 0; i < n; ++i)
@@ -587,7 +589,10 @@ static int run_forward(RtodPlan* p, const float* x, float* pred, int train, cuda
         rc = RTOD_OK;
         switch (d.type) {
         case RTOD_LAYER_CONV:
-            if (nd.stem)
+            if (nd.stem && x_u8)
+                rc = launch_stem_tc(nullptr, x_u8, p->batch, p->in_h, p->in_w, reinterpret_cast<const float*>(p->wa + nd.wf_off),
+                                    nd.args.bias, d.filters, d.leaky, nd.args.out, stream);
+            else if (nd.stem)
                 rc = launch_stem_conv(x, p->batch, p->in_c, p->in_h, p->in_w,
                                       reinterpret_cast<const float*>(p->wa + nd.wf_off), nd.args.bias, d.filters,
                                       d.size, d.stride, d.pad, d.leaky, nd.args.out, stream);
@@ -630,6 +635,10 @@ static int run_forward(RtodPlan* p, const float* x, float* pred, int train, cuda
 
 extern "C" int rtod_plan_forward(RtodPlan* p, const float* x, float* pred, int train, void* stream) {
     return run_forward(p, x, pred, train, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int rtod_plan_forward_u8(RtodPlan* p, const unsigned char* x_planes, float* pred, int train, void* stream) {
+    return run_forward(p, nullptr, pred, train, (cudaStream_t)stream, nullptr, nullptr, x_planes);
 }
 
 extern "C" int rtod_plan_forward_profile(RtodPlan* p, const float* x, float* pred, int train, void* stream_,

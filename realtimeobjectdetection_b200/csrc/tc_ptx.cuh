@@ -346,7 +346,7 @@ static inline CUtensorMapSwizzle swizzle_for(int bk) {
 }
 
 // tcgen05 kind::f16 instruction descriptor: fp32 accumulate, fp16 (format 0) or bf16 (format 1) operands, both K-major
-static inline uint32_t umma_idesc(int f16, int m, int n) {
+static __host__ __device__ inline uint32_t umma_idesc(int f16, int m, int n) {
     const uint32_t fmt = f16 ? 0u : 1u;
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }

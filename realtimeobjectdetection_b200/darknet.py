@@ -86,6 +86,11 @@ class _Plan:
             _lib.check(lib.rtod_plan_bind(self.handle, ws, lib.rtod_plan_workspace_bytes(self.handle),
                                           wa, lib.rtod_plan_weight_bytes(self.handle)))
         self.is_f16 = bool(lib.rtod_plan_is_f16(self.handle))
+        first = descs[0]
+        # uint8 frames go straight into the tcgen05 stem (stem_tc.cu) when the plan has one
+        self.takes_u8 = bool(self.is_f16 and in_c == 3 and first.type == _lib.LAYER_CONV and first.size == 3 and
+                             first.stride == 1 and first.pad == 1 and first.filters in (16, 32, 64) and
+                             in_w >= 160 and in_w % 16 == 0)
         # failure reporting without a sync: kernels store a code in this pinned, device-mapped int on time-out
         self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         with torch.cuda.device(device):
@@ -93,10 +98,13 @@ class _Plan:
                                                     torch.cuda.current_stream(device).cuda_stream))
         self.weight_version = None
         # CUDA graphs of the launch sequence, keyed by (input pointer, train): {"graph", "x", "pred"}.
-        # Key None = the staging graph (input copied into its own buffer first).
+        # Key (dtype, train) = the staging graph of that input type (input copied into its own buffer first).
         self.graphs = {}
         self.calls = 0
         self.last_used = 0
+
+    def forward_fn(self, x):
+        return self.lib.rtod_plan_forward_u8 if x.dtype == torch.uint8 else self.lib.rtod_plan_forward
 
     def raise_if_failed(self):
         """Raise (and re-arm the plan) if a kernel of an earlier forward reported a device-side failure."""
@@ -420,7 +428,11 @@ class Darknet(nn.Module):
             device = params.device if params is not None and params.is_cuda else \
                 torch.device("cuda", torch.cuda.current_device())
         x = x.detach()
-        if not x.is_cuda or x.dtype != torch.float32:
+        # uint8 [B, 3, H, W] planes (util.prep_frames(..., as_uint8=True)) mean value / 255 (src/util.py:396): the stem
+        # takes them as they are, the scale is folded into its weights
+        if x.dtype == torch.uint8:
+            x = x.to(device=device, non_blocking=True)
+        elif not x.is_cuda or x.dtype != torch.float32:
             x = x.to(device=device, dtype=torch.float32, non_blocking=True)
         x = x.contiguous()
         inp_dim = int(self.net_info["height"])                       # :258 -- read at every call
@@ -434,9 +446,11 @@ class Darknet(nn.Module):
             stream = torch.cuda.current_stream(device)
             self._sync_weights(plan, stream.cuda_stream)
             has_heads = plan.n_rows > 0
+            if x.dtype == torch.uint8 and not plan.takes_u8:
+                x = x.to(torch.float32) / 255.0                  # (bf16 storage / unusual stems: scale here)
             pred = self._run(plan, x, int(bool(self.TRAIN)), stream) if has_heads else None
             if not has_heads:
-                _lib.check(lib.rtod_plan_forward(plan.handle, x.data_ptr(), None, 0, stream.cuda_stream))
+                _lib.check(plan.forward_fn(x)(plan.handle, x.data_ptr(), None, 0, stream.cuda_stream))
 
         # side effects of the reference's yolo branch (:239-243, :260)
         anchors, classes = [], None
@@ -456,19 +470,20 @@ class Darknet(nn.Module):
         capturing = torch.cuda.is_current_stream_capturing()
         if not self.use_cuda_graph or capturing or plan.calls < 1:
             pred = torch.empty(shape, dtype=torch.float32, device=plan.device)
-            _lib.check(lib.rtod_plan_forward(plan.handle, x.data_ptr(), pred.data_ptr(), train,
-                                             stream.cuda_stream))
+            _lib.check(plan.forward_fn(x)(plan.handle, x.data_ptr(), pred.data_ptr(), train, stream.cuda_stream))
             return pred
         # The launch sequence is replayed as a CUDA graph.  A graph embeds its input pointer: inputs that keep
         # arriving in the same buffers (the pipeline's ring slots, a benchmark's resident batches) get a graph
         # of their own -- no staging copy; any other input is copied into the staging graph's buffer.
         entry = plan.graphs.get((x.data_ptr(), train))
+        if entry is not None and entry["x"].dtype != x.dtype:
+            entry = None
         if entry is None and self.borrow_output and len(plan.graphs) < 6:
             entry = self._capture(plan, x, train, stream, key=(x.data_ptr(), train))
         if entry is None:
-            entry = plan.graphs.get((None, train))
+            entry = plan.graphs.get((str(x.dtype), train))
             if entry is None:
-                entry = self._capture(plan, torch.empty_like(x), train, stream, key=(None, train))
+                entry = self._capture(plan, torch.empty_like(x), train, stream, key=(str(x.dtype), train))
             if entry is not None:
                 entry["x"].copy_(x, non_blocking=True)
         if entry is None:                                      # capture unsupported: stream launches
@@ -483,8 +498,8 @@ class Darknet(nn.Module):
         try:
             stream.synchronize()
             with torch.cuda.graph(entry["graph"]):
-                _lib.check(plan.lib.rtod_plan_forward(plan.handle, x.data_ptr(), entry["pred"].data_ptr(), train,
-                                                      torch.cuda.current_stream(plan.device).cuda_stream))
+                _lib.check(plan.forward_fn(x)(plan.handle, x.data_ptr(), entry["pred"].data_ptr(), train,
+                                              torch.cuda.current_stream(plan.device).cuda_stream))
         except Exception as exc:                              # capture unsupported: stay eager
             warnings.warn("CUDA graph capture failed (%s); using stream launches" % (exc,))
             self.use_cuda_graph = False

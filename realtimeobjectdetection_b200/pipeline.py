@@ -67,14 +67,15 @@ class DetectionPipeline:
         return s
 
     def _network_input(self, slot):
-        """the slot's frames as the fp32 [B, 3, D, D] tensor the network reads (a stable buffer per slot, so the
-        forward replays one CUDA graph per slot)"""
+        """the slot's frames as the tensor the network reads (a stable buffer per slot, so the forward replays one
+        CUDA graph per slot): fp32 [B, 3, D, D] as is; uint8 frames are letterboxed / channel-swapped on the device into
+        uint8 planes, which the stem consumes directly (value / 255 folded into its weights)"""
         if slot["buf"].dtype == torch.float32:
             return slot["buf"]
         dim = int(self.model.net_info["height"])
         if slot["x"] is None or slot["x"].size(2) != dim:
-            slot["x"] = torch.empty(slot["buf"].size(0), 3, dim, dim, dtype=torch.float32, device=self.device)
-        return prep_frames(slot["buf"], dim, "BGR", self.resize, out=slot["x"])
+            slot["x"] = torch.empty(slot["buf"].size(0), 3, dim, dim, dtype=torch.uint8, device=self.device)
+        return prep_frames(slot["buf"], dim, "BGR", self.resize, out=slot["x"], as_uint8=True)
 
     def run(self, host_batches):
         """host_batches: iterable of host tensors (pinned memory avoids a staging copy).  Yields
