@@ -369,6 +369,24 @@ def run_b200(args):
                            "Darknet.forward -> write_results -> host rows" % (RESO, RESO))
     host_f32 = [torch.rand(B, 3, RESO, RESO).pin_memory() for _ in range(2)]
     e2e_f32 = e2e_run(host_f32, "same pipeline fed pinned fp32 [B,3,%d,%d] host tensors (what prep_image returns)" % (RESO, RESO))
+    # device pre-processing alone (rtod_prep_image): frames at network resolution (identity resize) and 640x480 camera
+    # frames (cubic letterbox), uint8 planes out
+    from realtimeobjectdetection_b200.util import prep_frames
+    prep_times = {}
+    for tag, (fh, fw) in (("%dx%d" % (RESO, RESO), (RESO, RESO)), ("640x480", (480, 640))):
+        src = torch.randint(0, 256, (B, fh, fw, 3), dtype=torch.uint8, device=dev)
+        dst = torch.empty(B, 3, RESO, RESO, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            prep_frames(src, RESO, out=dst, as_uint8=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            prep_frames(src, RESO, out=dst, as_uint8=True)
+        e1.record()
+        torch.cuda.synchronize()
+        prep_times[tag] = e0.elapsed_time(e1) / 10
+        del src, dst
+    e2e["prep_ms_per_batch"] = prep_times
     del host_u8, host_f32
 
     # ---- roofline of the dominant kernel, measured live per layer --------------------------------

@@ -164,6 +164,9 @@ int rtod_plan_reset_errors(RtodPlan* plan, void* stream);
 int rtod_plan_is_f16(const RtodPlan* plan);
 /* 1 = convolution `layer` keeps two-term (hi + lo) weights */
 int rtod_plan_conv_w_split(const RtodPlan* plan, int layer);
+/* 1 if convolution `layer` of a bound plan runs in row mode (3x3 / stride 1 on the tcgen05 kernel: one tiled TMA load
+ * per filter row, the three kx taps as row-shifted views of it; csrc/conv_tc.cuh) */
+int rtod_plan_conv_row_mode(const RtodPlan* plan, int layer);
 
 /* ---- util.predict_transform (src/util.py:175-239) -------------------------------------
  * head: [B, A*(5+C), G, G] fp32 NCHW -> out: [B, G*G*A, 5+C] fp32; anchors_host: A (w,h) pixel

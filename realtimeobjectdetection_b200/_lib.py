@@ -73,6 +73,7 @@ _PROTOTYPES = {
     "rtod_plan_reset_errors": (_i, [_vp, _vp]),
     "rtod_plan_is_f16": (_i, [_vp]),
     "rtod_plan_conv_w_split": (_i, [_vp, _i]),
+    "rtod_plan_conv_row_mode": (_i, [_vp, _i]),
     "rtod_yolo_decode": (_i, [_vp, _i, _i, _i, _i, _i, ctypes.POINTER(_f), _i, _vp, _vp]),
     "rtod_write_results_workspace_bytes": (_sz, [_i, _i, _i]),
     "rtod_write_results": (_i, [_vp, _i, _i, _i, _f, _f, _vp, _i, _vp, _vp, _sz, _vp]),

@@ -26,7 +26,9 @@ static __device__ __forceinline__ uint32_t acc_column(const ConvTcParams& p, int
 }
 
 // ew: epilogue warp index (0 .. kEpiWarps-1; warps ew and ew+4 share a lane quarter)
-// origin(tile, m0, n0): first row / first channel of the tile in the output matrix
+// origin(tile, m0, n0, row): first row / first channel of the tile in the output matrix [M, Cout]; in row mode
+//   (p.row_mode: a tile is a segment of ONE image row) m0 is the segment's first column and `row` the image row
+//   b * Ho + y: output and shortcut operand are then addressed as {Cout, W, B*Ho}, columns beyond W are clipped
 // release(buf): arrive on the accumulator-empty barrier the MMA issuer waits on (called by one lane)
 // The TMA / bulk-group / mbarrier-arrive instructions of a warp are always issued by its elect.sync lane
 // (deterministic for a full mask), so the per-thread bulk async-groups stay with one thread.
@@ -46,10 +48,11 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
     const int halves = p.out_fp32 ? 1 : (ecols + 31) / 32;              // 32 accumulator columns each
 
     auto issue_res = [&](int tile, int c, uint32_t sb) {                 // elected lane only
-        int m0, n0;
-        origin(tile, m0, n0);
+        int m0, n0, row;
+        origin(tile, m0, n0, row);
         mbar_expect_tx(&my_res[sb], 32u * erow);
-        tma_load_2d(my_stage + sb * kEpiSlice, &p.tmRes, &my_res[sb], n0 + c * ecols, m0 + quarter * 32);
+        if (p.row_mode) tma_load_3d(my_stage + sb * kEpiSlice, &p.tmRes, &my_res[sb], n0 + c * ecols, m0 + quarter * 32, row);
+        else tma_load_2d(my_stage + sb * kEpiSlice, &p.tmRes, &my_res[sb], n0 + c * ecols, m0 + quarter * 32);
     };
     if (p.has_res && cg < n_chunks && tile_first < p.total_tiles && elect_one()) issue_res(tile_first, cg, 0u);
 
@@ -59,8 +62,8 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
     int local = 0;
     for (int tile = tile_first; tile < p.total_tiles; tile += tile_step, ++local) {
         const int buf = local & 1;
-        int m0, n0;
-        origin(tile, m0, n0);
+        int m0, n0, row;
+        origin(tile, m0, n0, row);
         mbar_wait(&acc_full[buf], (uint32_t)(local >> 1) & 1u, p.err_flag);
         tc_fence_after();
         if (cg >= n_chunks) {                            // tile narrower than the column groups: nothing to do
@@ -140,7 +143,8 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
             fence_async_smem();                          // generic-proxy writes -> visible to the TMA
             __syncwarp();
             if (elect_one()) {
-                if (!(p.dbg & 16)) tma_store_2d(&p.tmOut, slice, n0 + c * ecols, m0 + quarter * 32);
+                if (p.row_mode) tma_store_3d(&p.tmOut, slice, n0 + c * ecols, m0 + quarter * 32, row);
+                else if (!(p.dbg & 16)) tma_store_2d(&p.tmOut, slice, n0 + c * ecols, m0 + quarter * 32);
                 bulk_commit();
                 if (p.has_res) {                         // shortcut operand of this warp's next chunk
                     int nt = tile, nc = c + kColGroups;
@@ -189,8 +193,8 @@ static __device__ __forceinline__ void conv_epilogue_split(const ConvTcParams& p
     int tile, slice_k;
     for (int local = 0; work(local, tile, slice_k); ++local) {
         const int buf = local & 1;
-        int m0, n0;
-        origin(tile, m0, n0);
+        int m0, n0, image_row;
+        origin(tile, m0, n0, image_row);                    // (split-K is never combined with row mode)
         mbar_wait(&acc_full[buf], (uint32_t)(local >> 1) & 1u, p.err_flag);
         tc_fence_after();
         // ---- pass 1: raw accumulator -> scratch ----------------------------------------------------------

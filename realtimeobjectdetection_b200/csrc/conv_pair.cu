@@ -197,10 +197,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
         // ================= epilogue (conv_epilogue.cuh): each CTA stores its own 128 rows =================
         conv_epilogue<kEpilogueWarps, kF16>(
             p, tmem_base, acc_full, epi_stage, res_full, warp - 2, lane, tile_first, tile_step,
-            [&](int tile, int& m0, int& n0) {
+            [&](int tile, int& m0, int& n0, int& row) {
                 const int n_tile = (int)fast_div((uint32_t)tile, p.fd_mtiles);
                 m0 = (2 * (tile - n_tile * p.m_tiles) + (int)rank) * kBM;
                 n0 = n_tile * p.BN;
+                row = -1;
             },
             [&](int buf) {                               // the leader's MMA issuer waits for both CTAs' epilogues
                 if (rank == 0) mbar_arrive(&acc_empty[buf]);
@@ -250,7 +251,7 @@ int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     p.ks = a.ks; p.cchunks = a.Cin / BK; p.BK = BK; p.BN = BN;
     p.Ho = a.out.H; p.Wo = a.out.W; p.stride = a.stride; p.pad = a.pad;
     p.w_cat = a.w_split ? 1 : 0;
-    p.acc_cols = BN << p.w_cat; p.lo_col = BN / 2; p.subs = 1;
+    p.acc_cols = BN << p.w_cat; p.lo_col = BN / 2; p.subs = 1; p.row_mode = 0;
     p.tmem_cols = 2 * p.acc_cols; p.has_res = a.res != nullptr; p.ecols = 64; p.b_resident = 0; p.stage_bufs = 2;
     p.dbg = (getenv("RTOD_PAIR_MODE") ? atoi(getenv("RTOD_PAIR_MODE")) : 0) | (getenv("RTOD_CLK_DBG") ? 8 : 0);
     p.f16 = a.in.f16; p.w_split = a.w_split; p.cout_pad = a.Cout_pad;

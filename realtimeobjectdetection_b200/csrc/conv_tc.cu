@@ -33,6 +33,7 @@
 #include "conv_tc.cuh"
 #include "tc_ptx.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -43,6 +44,8 @@ namespace {
 constexpr int kFirstEpiWarp = 4;                // warps 0-3: TMA producer A, MMA issuer, TMA producer B, 2nd producer A
 constexpr int threads_for(int epi_warps, int subs = 1) { return 32 * (kFirstEpiWarp + epi_warps) * subs; }
 constexpr uint32_t kResidentLimit = 100 * 1024; // largest weight matrix kept resident in shared memory
+constexpr uint32_t kResidentLimitRow = 150 * 1024;   // row mode (always resident; its stages are small slabs)
+constexpr int kSlabRows = kBM + 2;              // row mode: input pixels x0-1 .. x0+128 of one image row
 
 // =============================================================================================
 // Persistent: one CTA per SM walks output tiles (m fastest, so concurrently running CTAs share the
@@ -76,7 +79,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
 #endif
     const uint32_t row_bytes = (uint32_t)p.BK * 2u;
     // weight tile of one k-block: BN rows, twice that (hi rows, then lo rows) for split weights
-    const uint32_t a_bytes = kBM * row_bytes, b_half = (uint32_t)p.BN * row_bytes, b_bytes = b_half << p.w_split;
+    // (row mode: the A part of a stage is one slab of 130 input pixels, see ConvTcParams::row_mode)
+    const uint32_t a_bytes = p.row_mode ? p.slab_bytes : kBM * row_bytes;
+    const uint32_t b_half = (uint32_t)p.BN * row_bytes, b_bytes = b_half << p.w_split;
     const uint32_t stage_bytes = a_bytes + (p.b_resident ? 0u : b_bytes);
     // ring stages (one ring per pipeline) hold {A, B} tiles, or A tiles only when the whole weight matrix is resident
     uint8_t* ring = smem + (size_t)sub * p.stages * stage_bytes;
@@ -171,6 +176,31 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
             const int cin = p.cchunks * p.BK;
             TRACE_DECL(dbg_wait);
             TRACE_T0(dbg_start);
+            if (p.row_mode) {
+                // one tiled load per (filter row, channel slice): input pixels x0-1 .. x0+128 of image row y-1+ky; the
+                // descriptor zero-fills x = -1, x >= W, y = -1 and y = H (4-D map {C, W, H, B}: no bleed between images)
+                const uint32_t slab_tx = (uint32_t)kSlabRows * row_bytes;
+                for (int tile = first_item; ok && tile < n_items; tile += item_step) {
+                    const int n_tile = (int)fast_div((uint32_t)tile, p.fd_mtiles);
+                    const int m_tile = tile - n_tile * p.m_tiles;
+                    const int rowi = (int)fast_div((uint32_t)m_tile, p.fd_segs);
+                    const int x0 = (m_tile - rowi * p.segs) * kBM - 1;
+                    const int b = (int)fast_div((uint32_t)rowi, p.fd_ho);
+                    const int y = rowi - b * p.Ho - 1;
+                    for (int ky = 0; ok && ky < 3; ++ky)
+                        for (int c0 = 0; c0 < cin; c0 += p.BK) {
+                            TRACE_T0(w0);
+                            if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag)) { ok = false; break; }
+                            TRACE_ADD(dbg_wait, w0);
+                            mbar_expect_tx(&full_bar[stage], slab_tx);
+                            tma_load_4d(ring + (size_t)stage * stage_bytes, &p.tmA, &full_bar[stage], c0, x0, y + ky, b);
+                            if (++stage == p.stages) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                        }
+                }
+            } else
             for (int item = first_item; ok && item < n_items; item += item_step) {
                 const int tile = item >> p.split_shift;
                 const int kb0 = (item & (p.split_k - 1)) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
@@ -212,7 +242,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
                 }
             }
 #ifdef RTOD_TC_TRACE
-            if ((p.dbg & 16) && blockIdx.x == 0)
+            if ((p.dbg & 64) && blockIdx.x == 0)
                 printf("  tc producer %d: total %lld clk, waiting for empty %lld, tiles %d x %d k-blocks, stages %d, grid %d\n", me,
                        clock64() - dbg_start, dbg_wait, (p.total_tiles + item_step - 1) / item_step, num_kb, p.stages, (int)gridDim.x);
 #endif
@@ -264,6 +294,58 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
             TRACE_DECL(dbg_wfull);
             TRACE_T0(dbg_start);
             if (p.b_resident) ok = mbar_wait(wres_bar, 0u, p.err_flag);
+            if (p.row_mode) {
+                // per staged slab (filter row ky, channel slice c): the three kx taps are the slab shifted by 0 / 1 / 2 pixel
+                // rows -- a UMMA descriptor may start at any row of a swizzled tile (tools/umma_shift*_probe.cu)
+                for (int tile = first_item; ok && tile < n_items; tile += item_step, ++local) {
+                    const int buf = local & 1;
+                    TRACE_T0(w0);
+                    if (!mbar_wait(&acc_empty[buf], ((uint32_t)(local >> 1) & 1u) ^ 1u, p.err_flag)) break;
+                    TRACE_ADD(dbg_wacc, w0);
+                    tc_fence_after();
+                    const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * p.acc_cols);
+                    uint32_t first = 0;
+                    for (int ky = 0; ok && ky < 3; ++ky) {
+                        // the channel slices of this filter row sit in consecutive stages; the MMAs run kx-major over all of
+                        // them -- the K order of the im2col path (ky, kx, channel), hence bit-identical results
+                        int st = stage;
+                        uint32_t ph = phase;
+                        TRACE_T0(w1);
+                        for (int c = 0; c < p.cchunks; ++c) {
+                            if (!mbar_wait(&full_bar[st], ph, p.err_flag)) { ok = false; break; }
+                            if (++st == p.stages) {
+                                st = 0;
+                                ph ^= 1u;
+                            }
+                        }
+                        if (!ok) break;
+                        TRACE_ADD(dbg_wfull, w1);
+                        if (local == 0 && first == 0) { TRACE_STAMP(3); }
+                        tc_fence_after();
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            int sc = stage;
+                            for (int c = 0; c < p.cchunks; ++c) {
+                                const uint32_t a_addr = ring_base + (uint32_t)sc * stage_bytes + (uint32_t)kx * row_bytes;
+                                const uint32_t b_addr = wres_base + (uint32_t)((ky * 3 + kx) * p.cchunks + c) * b_bytes;
+                                uint64_t da = desc_tmpl | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+                                uint64_t db = desc_tmpl | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
+                                for (int k = 0; k < ksteps; ++k, da += 2, db += 2, first = 1)
+                                    umma_bf16(tmem_acc, da, db, p.idesc, first);
+                                if (++sc == p.stages) sc = 0;
+                            }
+                        }
+                        for (int c = 0, sc = stage; c < p.cchunks; ++c) {
+                            umma_commit(&empty_bar[sc]);
+                            if (++sc == p.stages) sc = 0;
+                        }
+                        stage = st;
+                        phase = ph;
+                    }
+                    umma_commit(&acc_full[buf]);
+                    if (local == 0) { TRACE_STAMP(4); }
+                }
+            } else
             for (int item = first_item; ok && item < n_items; item += item_step, ++local) {
                 const int kb0 = (item & (p.split_k - 1)) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
                 const int buf = local & 1;
@@ -298,17 +380,24 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
             }
             TRACE_STAMP(5);
 #ifdef RTOD_TC_TRACE
-            if ((p.dbg & 16) && blockIdx.x == 0)
+            if ((p.dbg & 64) && blockIdx.x == 0)
                 printf("  tc mma: total %lld clk, waiting for full %lld, for acc_empty %lld (BN %d BK %d resident %d epi_warps %d)\n",
                        clock64() - dbg_start, dbg_wfull, dbg_wacc, p.BN, p.BK, p.b_resident, p.epi_warps);
 #endif
         }
     } else {
         // ================= epilogue (conv_epilogue.cuh) =================
-        auto origin = [&](int tile, int& m0, int& n0) {
+        auto origin = [&](int tile, int& m0, int& n0, int& row) {
             const int n_tile = (int)fast_div((uint32_t)tile, p.fd_mtiles);
-            m0 = (tile - n_tile * p.m_tiles) * kBM;
+            const int m_tile = tile - n_tile * p.m_tiles;
             n0 = n_tile * p.BN;
+            if (p.row_mode) {
+                row = (int)fast_div((uint32_t)m_tile, p.fd_segs);        // b * Ho + y
+                m0 = (m_tile - row * p.segs) * kBM;                      // first column of the segment
+            } else {
+                m0 = m_tile * kBM;
+                row = -1;
+            }
         };
         auto release = [&](int buf) { mbar_arrive(&acc_empty[buf]); };
         if (p.split_k > 1)
@@ -378,12 +467,29 @@ bool conv_tc_supported(const ConvArgs& a) {
     return true;
 }
 
+// row mode (ConvTcParams::row_mode): 3x3 / stride 1 / pad 1, input channels in 64-byte slices, the whole (two-term)
+// weight matrix resident in shared memory next to at least three slabs
+bool conv_tc_row_eligible(const ConvArgs& a) {
+    if (a.ks != 3 || a.stride != 1 || a.pad != 1 || a.Cin % 32 != 0 || a.out.fp32) return false;
+    if (a.Cout_pad > (a.w_split ? 128 : 256)) return false;
+    return (uint32_t)(a.Cout_pad << a.w_split) * a.K * 2 <= kResidentLimitRow;
+}
+
 int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, const ConvTcChoice* force) {
     if (!conv_tc_supported(a)) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: unsupported convolution shape");
     launch->patch = 0;
-    launch->p.dbg = getenv("RTOD_CLK_DBG") ? 8 : 0;
-    if (force ? force->pair == 1 : conv_pair_eligible(a)) {
-        if (!conv_pair_eligible(a)) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: CTA-pair kernel not applicable");
+    launch->p.dbg = getenv("RTOD_CLK_DBG") ? (atoi(getenv("RTOD_CLK_DBG")) >= 2 ? 8 | 64 : 8) : 0;   // 2: per-role wait counters too
+    // row mode (ConvTcParams::row_mode): 3x3 / stride 1 layers with few input channels; a third of the gather's L2 -> SM
+    // bytes and TMA rows, but a tile is a segment of ONE image row (104 / 208-pixel rows waste 19 / 23 % of the MMA rows).
+    // Chosen by the autotuner when it measures faster (`force`) or by RTOD_TC_ROW; the heuristic never picks it:
+    // at YOLOv3-416 batch 64 these layers are bound by the shared-memory feed of the narrow-N MMAs, not by the gather
+    // (measured: 32->64 @208: 263 vs 235 us, 64->128 @104: 204 vs 122 us).
+    const bool row_ok = conv_tc_row_eligible(a);
+    int row = force ? force->row : 0;
+    if (const char* e = getenv("RTOD_TC_ROW")) row = atoi(e) && row_ok ? 1 : 0;
+    if (row && !row_ok) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: row mode not applicable");
+    if (force ? force->pair == 1 : (!row && conv_pair_eligible(a))) {
+        if (!conv_pair_eligible(a) || row) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: CTA-pair kernel not applicable");
         return conv_pair_prepare(a, err_flag, launch);
     }
     static EncodeTiledFn encode_tiled = nullptr;
@@ -395,13 +501,13 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
         if (rc) return rc;
     }
     ConvTcParams& p = launch->p;
-    const int BK = pick_bk(a.Cin);
+    const int BK = row ? 32 : pick_bk(a.Cin);
     int BN = a.Cout_pad < 256 ? a.Cout_pad : 256;       // widest tile the single-CTA MMA supports
     if (a.Cout_pad % BN != 0) BN = 128;
     // two-term weights always run as one concatenated MMA of N = 2*BN <= 256 (w_cat): the hi and lo products are
     // added in the epilogue, so the rounding -- unlike the tile shape -- must not depend on the configuration
     if (a.w_split && BN > 128) BN = 128;
-    {   // small batches: a layer must still spread over the 148 SMs -> narrower N tiles
+    if (!row) {   // small batches: a layer must still spread over the 148 SMs -> narrower N tiles
         const long long m_tiles = ((long long)a.B * a.out.H * a.out.W + kBM - 1) / kBM;
         while (BN > 32 && m_tiles * (a.Cout_pad / BN) < 120 && a.Cout_pad % (BN / 2) == 0) BN /= 2;
     }
@@ -416,6 +522,7 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
     }
     if (a.Cout_pad % BN != 0 || BN % 32 != 0)
         return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: Cout_pad %d not tileable", a.Cout_pad);
+    if (row && BN != a.Cout_pad) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: row mode needs a single N tile");
     const long long M = (long long)a.B * a.out.H * a.out.W;
     p.bias = a.bias;
     p.err_flag = err_flag;
@@ -452,8 +559,13 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
     // resident weights if that is what makes them fit; fat tiles (BN = 256) keep one CTA per SM,
     // eight epilogue warps and the deepest operand ring that fits.
     const uint32_t w_bytes = (uint32_t)(BN << a.w_split) * a.K * 2;
-    const bool may_reside = a.Cout_pad == BN && w_bytes <= kResidentLimit && getenv("RTOD_TC_NO_RESIDENT") == nullptr;
-    const uint32_t a_stage = (uint32_t)kBM * BK * 2;
+    const bool may_reside = a.Cout_pad == BN && w_bytes <= (row ? kResidentLimitRow : kResidentLimit) &&
+                            (row || getenv("RTOD_TC_NO_RESIDENT") == nullptr);
+    p.row_mode = row;
+    p.slab_bytes = ((uint32_t)kSlabRows * BK * 2 + 1023u) & ~1023u;
+    p.segs = (a.out.W + kBM - 1) / kBM;
+    const uint32_t a_stage = row ? p.slab_bytes : (uint32_t)kBM * BK * 2;
+    if (row && !may_reside) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: row mode needs resident weights");
     if (subs == 2 && (2 * cols > 512 || a.Cout_pad != BN || w_bytes > 2 * kResidentLimit || getenv("RTOD_TC_NO_RESIDENT")))
         return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: dual pipeline needs resident weights and 2 x %d TMEM columns", cols);
     int max_ctas = subs == 2 ? 1 : 512 / cols;
@@ -479,12 +591,12 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
         for (int opt = 0; opt < 4 && stages == 0; ++opt) {
             const bool resident = (may_reside || subs == 2) && (opt & 1) == 0;      // (dual: weights up to 2 x the limit)
             const int sbufs = (opt & 2) ? 1 : 2;
-            if ((opt & 1) && (may_reside == false || subs == 2)) continue;
+            if ((opt & 1) && (may_reside == false || subs == 2 || row)) continue;
             if (force && (force->resident != (resident ? 1 : 0) || force->sbufs != sbufs)) continue;
             if (env_sb && atoi(env_sb) != sbufs) continue;
             const uint32_t fx = 1024 + subs * ew * sbufs * kEpiSlice + 512 * subs + (resident ? w_bytes : 0);
             const uint32_t sb = (resident ? a_stage : stage_bytes) * subs;         // one ring per pipeline
-            const int want = (ctas == 1 && subs == 1) ? 2 : 3;
+            const int want = row ? std::max(3, a.Cin / BK + 1) : ((ctas == 1 && subs == 1) ? 2 : 3);
             if (fx + want * sb > cap) continue;
             ctas_per_sm = ctas;
             epi_warps = ew;
@@ -510,19 +622,19 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
                 (unsigned long long)tiles * split * kBM * BN * 4ull > a.split_scratch_bytes)
                 return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: split-K %d not applicable", split);
         }
-        if (split > 1 && subs == 2) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: no split-K on the dual pipeline");
+        if (split > 1 && (subs == 2 || row)) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: no split-K on the dual pipeline / in row mode");
         p.split_k = split;
         p.split_shift = split == 8 ? 3 : (split == 4 ? 2 : (split == 2 ? 1 : 0));
         p.split_scratch = a.split_scratch;
         p.split_count = a.split_count;
     }
-    launch->choice = ConvTcChoice{ctas_per_sm, p.b_resident, p.stage_bufs, 0, BN, p.split_k, epi_warps, p.a_producers, subs};
     // im2col issue costs a thread ~350 cycles: two alternating A producers when a k-block's MMAs take less
-    p.a_producers = (a.ks > 1 && (BK / 16) * (BN / 2) < 350 && getenv("RTOD_TC_ONE_A") == nullptr) ? 2 : 1;
+    p.a_producers = (a.ks > 1 && !row && (BK / 16) * (BN / 2) < 350 && getenv("RTOD_TC_ONE_A") == nullptr) ? 2 : 1;
     if (force && force->ap) {
-        if (force->ap == 2 && (a.ks == 1 || stages < 2)) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: two activation producers need a gather");
+        if (force->ap == 2 && (a.ks == 1 || stages < 2 || row)) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: two activation producers need a gather");
         p.a_producers = force->ap;
     }
+    launch->choice = ConvTcChoice{ctas_per_sm, p.b_resident, p.stage_bufs, 0, BN, p.split_k, epi_warps, p.a_producers, subs, row};
     {   // channels per epilogue chunk: one 128-byte staging row, narrower if the tile has fewer columns per group
         const int per_group = BN / (epi_warps / 4);
         p.ecols = a.out.fp32 ? 32 : (per_group < 64 ? per_group : 64);
@@ -533,10 +645,13 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
         if (v >= 2 && v < stages) stages = v;
     }
     if (stages < 2) stages = 2;
+    if (row && stages < a.Cin / BK + 1) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: row mode needs more stages than channel slices");
     p.stages = stages;                                   // per pipeline (stage_bytes_eff covers all pipelines)
-    p.m_tiles = (int)((M + kBM - 1) / kBM);
+    p.m_tiles = row ? a.B * a.out.H * p.segs : (int)((M + kBM - 1) / kBM);
     p.total_tiles = p.m_tiles * (a.Cout_pad / BN);
     store_fastdiv(p.fd_mtiles, (uint32_t)p.m_tiles);
+    store_fastdiv(p.fd_segs, (uint32_t)p.segs);
+    store_fastdiv(p.fd_ho, (uint32_t)a.out.H);
     store_fastdiv(p.fd_wo, (uint32_t)a.out.W);
     store_fastdiv(p.fd_howo, (uint32_t)(a.out.W * a.out.H));
     launch->smem_bytes = stages * stage_bytes_eff + fixed;
@@ -549,7 +664,15 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
     // ---- A ----
     const cuuint32_t estr1[4] = {1, 1, 1, 1};
     CUresult r;
-    if (a.ks == 1) {
+    if (row) {
+        const cuuint64_t dims[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.in.W, (cuuint64_t)a.in.H, (cuuint64_t)a.B};
+        const cuuint64_t strides[3] = {(cuuint64_t)a.in.pitch * 2, (cuuint64_t)a.in.pitch * 2 * a.in.W,
+                                       (cuuint64_t)a.in.pitch * 2 * a.in.W * a.in.H};
+        const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)kSlabRows, 1, 1};
+        r = encode_tiled(&p.tmA, h16_tmap_type(a.in.f16), 4, a.in.ptr, dims, strides, box, estr1,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (a.ks == 1) {
         const cuuint64_t dims[2] = {(cuuint64_t)a.Cin, (cuuint64_t)M};
         const cuuint64_t strides[1] = {(cuuint64_t)a.in.pitch * 2};
         const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)kBM};
@@ -570,7 +693,7 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
                           swizzle_for(BK), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
-    if (r == CUDA_SUCCESS && a.ks > 1 &&
+    if (r == CUDA_SUCCESS && a.ks > 1 && !row &&
         (unsigned long long)a.in.pitch * 2ull * a.in.W * a.in.H * a.B < 131072ull) {
         // im2col descriptors of tensors smaller than 128 KiB: drivers up to CUDA 13.1 set bit 21 of
         // the second descriptor word, which must be clear (same fix-up CUTLASS applies)
@@ -596,17 +719,19 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
         const size_t esz = a.out.fp32 ? 4 : 2;
         const CUtensorMapDataType dt = a.out.fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : h16_tmap_type(a.in.f16);
         const CUtensorMapSwizzle sw = p.ecols * esz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-        const cuuint64_t dims[2] = {(cuuint64_t)a.Cout, (cuuint64_t)M};
-        const cuuint64_t strides[1] = {(cuuint64_t)a.out.pitch * esz};
-        const cuuint32_t box[2] = {(cuuint32_t)p.ecols, 32};       // one epilogue warp's rows
-        r = encode_tiled(&p.tmOut, dt, 2, a.out.ptr, dims, strides, box, estr1, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+        // row mode: {Cout, W, B*Ho} so that a segment's rows beyond the image width are clipped (stores) / zero (loads)
+        const cuuint32_t rank = row ? 3 : 2;
+        const cuuint64_t dims[3] = {(cuuint64_t)a.Cout, (cuuint64_t)(row ? a.out.W : M), (cuuint64_t)a.B * a.out.H};
+        const cuuint64_t strides[2] = {(cuuint64_t)a.out.pitch * esz, (cuuint64_t)a.out.pitch * esz * a.out.W};
+        const cuuint32_t box[3] = {(cuuint32_t)p.ecols, 32, 1};    // one epilogue warp's rows
+        r = encode_tiled(&p.tmOut, dt, rank, a.out.ptr, dims, strides, box, estr1, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS)
             return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (output, Cout=%d pitch=%d) failed: %d", a.Cout,
                         a.out.pitch, (int)r);
         if (p.has_res) {
-            const cuuint64_t rstrides[1] = {(cuuint64_t)a.res_pitch * 2};
-            r = encode_tiled(&p.tmRes, h16_tmap_type(a.in.f16), 2, const_cast<void*>(a.res), dims,
+            const cuuint64_t rstrides[2] = {(cuuint64_t)a.res_pitch * 2, (cuuint64_t)a.res_pitch * 2 * a.out.W};
+            r = encode_tiled(&p.tmRes, h16_tmap_type(a.in.f16), rank, const_cast<void*>(a.res), dims,
                              rstrides, box, estr1, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS)
@@ -630,7 +755,7 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
 int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cudaStream_t stream) {
     if (const char* f = getenv("RTOD_TC_FORCE")) {       // tests: "pair,bn,ctas,resident,sbufs" -> exactly that candidate
         ConvTcChoice c{};
-        if (sscanf(f, "%d,%d,%d,%d,%d,%d,%d", &c.pair, &c.bn, &c.ctas, &c.resident, &c.sbufs, &c.split, &c.subs) >= 5 &&
+        if (sscanf(f, "%d,%d,%d,%d,%d,%d,%d,%d", &c.pair, &c.bn, &c.ctas, &c.resident, &c.sbufs, &c.split, &c.subs, &c.row) >= 5 &&
             conv_tc_prepare(a, err_flag, launch, &c) == RTOD_OK)
             return RTOD_OK;                              // (a candidate that does not fit falls through to the default)
     }
@@ -656,6 +781,7 @@ int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cud
         }
         return RTOD_OK;
     };
+    const bool row_ok = conv_tc_row_eligible(a);
     for (int pair = 1; pair >= 0; --pair)
       for (int bn = 256; bn >= 32; bn >>= 1)
         for (int ctas = 3; ctas >= 1; --ctas)
@@ -663,14 +789,16 @@ int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cud
                 for (int sbufs = 2; sbufs >= 1; --sbufs) {
                     if (pair && (bn != 256 || ctas != 1 || resident != 0 || sbufs != 2)) continue;   // one pair configuration (its N tile follows Cout)
                     if (!pair && bn > a.Cout_pad) continue;
-                    if (sbufs == 1 && a.res) continue;       // the shortcut operand is prefetched into the 2nd slice
                   for (int ew = 4; ew <= 8; ew += 4)
                    for (int ap = 1; ap <= 2; ++ap)
-                    for (int subs = 1; subs <= 2; ++subs) {
+                    for (int subs = 1; subs <= 2; ++subs)
+                     for (int row = 0; row <= (row_ok ? 1 : 0); ++row) {
+                    if (sbufs == 1 && a.res && !row) continue;   // the shortcut operand is prefetched into the 2nd slice
+                    if (row && (pair || !resident || ap != 1 || bn != a.Cout_pad)) continue;
                     if (pair && (ew != 8 || ap != 1 || subs != 1)) continue;
                     if (!pair && ((ew == 8 && (bn < 128 || ctas == 3)) || (ap == 2 && a.ks == 1))) continue;
                     if (subs == 2 && (ctas != 1 || ew != 4 || !resident)) continue;      // dual pipeline: one CTA, shared resident weights
-                    const ConvTcChoice c{ctas, resident, sbufs, pair, bn, 0, pair ? 0 : ew, pair ? 0 : ap, subs};
+                    const ConvTcChoice c{ctas, resident, sbufs, pair, bn, 0, pair ? 0 : ew, pair ? 0 : ap, subs, row};
                     cand = ConvTcLaunch{};
                     if (conv_tc_prepare(a, err_flag, &cand, &c) != RTOD_OK) continue;      // does not fit / apply
                     float ms;
@@ -686,10 +814,10 @@ int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cud
     if (rc) return rc;
     *launch = best;
     if (getenv("RTOD_TC_TUNE_DBG"))
-        fprintf(stderr, "conv_tc_autotune: M %d Cin %d Cout %d ks %d s %d -> %s BN %d ctas %d resident %d sbufs %d split %d epi %d aprod %d stages %d pipelines %d (%.1f us)\n",
+        fprintf(stderr, "conv_tc_autotune: M %d Cin %d Cout %d ks %d s %d -> %s BN %d ctas %d resident %d sbufs %d split %d epi %d aprod %d stages %d pipelines %d row %d (%.1f us)\n",
                 a.B * a.out.H * a.out.W, a.Cin, a.Cout, a.ks, a.stride, best.patch == 2 ? "pair" : "tc", best.choice.bn, best.choice.ctas,
                 best.choice.resident, best.choice.sbufs, best.choice.split, best.p.epi_warps, best.p.a_producers, best.p.stages,
-                best.p.subs, best_ms * 1e3f);
+                best.p.subs, best.p.row_mode, best_ms * 1e3f);
     return RTOD_OK;
 }
 

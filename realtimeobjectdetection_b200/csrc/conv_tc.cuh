@@ -39,6 +39,12 @@ struct alignas(64) ConvTcParams {
                                 // TMEM columns, added by the epilogue): half the MMA instructions; needs 2*BN <= 256
     int acc_cols;               // TMEM columns of one accumulator buffer: BN << w_cat
     int subs;                   // pipelines (warp sets) per CTA: 1, or 2 sharing the resident weights
+    // row mode (3x3 / stride 1, Cin == BK): a tile is a 128-pixel segment of ONE image row; per filter row ky one TILED
+    // TMA load brings the segment's 130 input pixels (halo and image border zero-filled) and the three kx taps are
+    // three row-shifted views of that slab -- a third of the TMA rows and of the L2 -> SM bytes of the im2col gather
+    int row_mode, segs;         // segs = ceil(Wo / 128) segments per image row
+    uint32_t slab_bytes;        // one staged slab: 130 rows, rounded up to 1024
+    uint32_t fd_segs[3], fd_ho[3];
     int lo_col;                 // column distance from a value's hi term to its lo term (w_cat): BN, pair kernel BN / 2
     int split_k, split_shift;   // K slices per output tile (power of two, 1 = off) and log2 of it
     float* split_scratch;       // [total_tiles][split_k][128][BN] fp32 partial accumulators
@@ -52,6 +58,7 @@ struct ConvTcChoice {           // one launch configuration of conv_tc_kernel (o
     int split;                  // K slices per tile (0 = by shape)
     int ew, ap;                 // epilogue warps (4 / 8), activation producer threads (1 / 2); 0 = heuristic
     int subs;                   // 2 = dual pipeline (two warp sets sharing resident weights in one CTA); 0 / 1 = single
+    int row;                    // 1 = row mode (ConvTcParams::row_mode)
 };
 
 struct ConvTcLaunch {           // host side: kernel parameters + launch geometry
@@ -71,6 +78,7 @@ int conv_pair_launch(const ConvTcLaunch& launch, cudaStream_t stream);
 int conv_split_factor(const ConvArgs& a);
 // true if the tensor-core kernel tiles this convolution
 bool conv_tc_supported(const ConvArgs& a);
+bool conv_tc_row_eligible(const ConvArgs& a);
 // fills `p` (encodes the TMA descriptors); `err_flag` is a device int
 int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, const ConvTcChoice* force = nullptr);
 // conv_tc_prepare + timing of every configuration that fits (plan-bind time); keeps the fastest

@@ -753,6 +753,11 @@ extern "C" int rtod_plan_conv_w_split(const RtodPlan* p, int layer) {
     return p->nodes[layer].w_split;
 }
 
+extern "C" int rtod_plan_conv_row_mode(const RtodPlan* p, int layer) {
+    if (!p || !p->bound || layer < 0 || layer >= (int)p->nodes.size() || p->nodes[layer].d.type != RTOD_LAYER_CONV) return 0;
+    return p->nodes[layer].use_tc ? p->nodes[layer].tc.p.row_mode : 0;
+}
+
 extern "C" int rtod_plan_check(RtodPlan* p, void* stream) {
     if (!p || !p->bound) return fail(RTOD_ERR_STATE, "rtod_plan_check: plan is not bound");
     int flag = 0;

@@ -46,6 +46,7 @@ struct PrepParams {
     int new_w, new_h, left, top;   // letterbox geometry (src/util.py:360-369)
     double scale_x, scale_y;       // source pixels per destination pixel
     int reverse;                   // 1: output channel c = source channel 2 - c (BGR -> RGB)
+    int identity;                  // the frame already has the network's size: the cubic weights are exactly {0, 1, 0, 0}
 };
 
 // kFixed: OpenCV's own path (11-bit fixed-point weights, int32 horizontal pass, fp32 vertical pass added
@@ -58,7 +59,10 @@ __global__ void __launch_bounds__(256) prep_image_kernel(const PrepParams p) {
         const int x = (int)(i % p.dim), y = (int)((i / p.dim) % p.dim), b = (int)(i / ((long long)p.dim * p.dim));
         int v[3] = {128, 128, 128};                                           // np.full(..., 128)
         const int dx = x - p.left, dy = y - p.top;
-        if (dx >= 0 && dx < p.new_w && dy >= 0 && dy < p.new_h) {
+        if (p.identity) {
+            const unsigned char* px = p.src + (((long long)b * p.src_h + y) * p.src_w + x) * 3;
+            v[0] = px[0]; v[1] = px[1]; v[2] = px[2];
+        } else if (dx >= 0 && dx < p.new_w && dy >= 0 && dy < p.new_h) {
             float cx[4], cy[4];
             const int sx = axis_entry(dx, p.scale_x, cx), sy = axis_entry(dy, p.scale_y, cy);
             const unsigned char* img = p.src + (long long)b * p.src_h * p.src_w * 3;
@@ -202,6 +206,7 @@ extern "C" int rtod_prep_image(const unsigned char* src, int B, int src_h, int s
     rtod_letterbox_geometry(src_w, src_h, inp_dim, &p.new_w, &p.new_h, &p.left, &p.top);
     if (p.new_w < 1 || p.new_h < 1)
         return fail(RTOD_ERR_UNSUPPORTED, "rtod_prep_image: %dx%d collapses at %d", src_w, src_h, inp_dim);
+    p.identity = (p.new_w == src_w && p.new_h == src_h && src_w == inp_dim && src_h == inp_dim) ? 1 : 0;
     p.scale_x = 1.0 / ((double)p.new_w / (double)src_w);                  // resize.cpp: scale = 1 / (dsize / ssize)
     p.scale_y = 1.0 / ((double)p.new_h / (double)src_h);
     const long long total = (long long)B * inp_dim * inp_dim;

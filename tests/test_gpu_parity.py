@@ -195,6 +195,7 @@ def run_block(lib, descs, x, weights, flags=0, backends=None, splits=None, confi
             if lib.rtod_plan_conv_config(plan, i, cfg12) == 0:
                 configs.append(dict(zip(("backend", "bn", "ctas", "resident", "sbufs", "split_k", "epi_warps", "a_producers",
                                          "pipelines", "stages", "w_split", "grid"), list(cfg12))))
+                configs[-1]["row"] = lib.rtod_plan_conv_row_mode(plan, i)
     outs = []
     for i in range(len(descs)):
         c, h, w = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
@@ -345,6 +346,69 @@ def test_residual_block_dual_pipeline(lib, monkeypatch):
     assert frac_within(outs[0], ref_block(x, w0, 3, 1, True, "fp16", split=True), *tol) == 1.0
     assert frac_within(outs[1], ref_block(outs[0], w1, 1, 1, True, "fp16", split=True), *tol) == 1.0
     assert frac_within(outs[3], ref_block(outs[1], w2, 3, 1, True, "fp16", split=True) + outs[0], *tol) == 1.0
+
+
+# row mode (3x3 / stride 1, few input channels): a tile is a 128-pixel segment of one image row, one tiled TMA load per
+# (filter row, 32-channel slice), the three kx taps as row-shifted views of the staged slab.  Images wider / narrower than
+# a segment, ragged last segments, one and two channel slices, two-term weights, both pipelines counts.
+ROW_CASES = [(32, 64, 136, 2, 64), (32, 64, 40, 3, 64), (64, 128, 104, 1, 128), (64, 64, 129, 1, 64), (32, 32, 260, 1, 32),
+             (128, 32, 50, 2, 32)]
+
+
+@pytest.mark.parametrize("cin,cout,H,batch,bn", ROW_CASES)
+@pytest.mark.parametrize("split", [0, 1])
+@pytest.mark.parametrize("dtype,dflag", DTYPES)
+def test_conv_block_row_mode(lib, monkeypatch, cin, cout, H, batch, bn, split, dtype, dflag):
+    if split and dtype == "bf16":
+        pytest.skip("two-term weights are an fp16 feature")
+    if (cout << split) * cin * 9 * 2 > 150 * 1024:
+        pytest.skip("row mode keeps the whole weight matrix in shared memory")
+    monkeypatch.setenv("RTOD_WSPLIT_ELEMS", "0")
+    monkeypatch.setenv("RTOD_WSPLIT_AI", "10000" if split else "0")
+    rng = np.random.RandomState(cin * 13 + cout + H)
+    x = torch.from_numpy(rng.randn(batch, cin, H, H).astype(np.float32))
+    w = rand_conv(rng, cin, cout, 3)
+    outs = []
+    for force in ("0,%d,1,1,2,0,1,1" % bn, "0,%d,1,1,1,0,1,1" % bn, "0,%d,1,1,2,0,2,1" % bn):
+        monkeypatch.setenv("RTOD_TC_FORCE", force)
+        cfgs = []
+        got = run_block(lib, [conv_desc(cout, 3, 1)], x, {0: w}, dflag, configs=cfgs)[0]
+        assert cfgs[0]["w_split"] == split
+        if cfgs[0]["row"] == 1:                          # (a configuration that does not fit falls back to the default)
+            assert cfgs[0]["resident"] == 1
+            outs.append(got)
+    assert len(outs) >= 1
+    monkeypatch.setenv("RTOD_TC_FORCE", "0,%d,1,0,2,0,1,0" % bn)
+    cfgs = []
+    gather = run_block(lib, [conv_desc(cout, 3, 1)], x, {0: w}, dflag, configs=cfgs)[0]
+    assert cfgs[0]["row"] == 0
+    monkeypatch.delenv("RTOD_TC_FORCE")
+    ref_q = ref_block(x, w, 3, 1, True, dtype, split=bool(split))
+    assert frac_within(gather, ref_q, *BLOCK_TOL[dtype]) == 1.0
+    for o in outs:                                       # same K order as the im2col gather: bit-identical
+        assert torch.equal(o, gather)
+
+
+def test_residual_block_row_mode(lib, monkeypatch):
+    rng = np.random.RandomState(37)
+    x = torch.from_numpy(rng.randn(2, 64, 104, 104).astype(np.float32))
+    w0, w1, w2 = rand_conv(rng, 64, 128, 3), rand_conv(rng, 128, 64, 1), rand_conv(rng, 64, 128, 3)
+    sc = _lib.RtodLayerDesc()
+    sc.type, sc.src0, sc.src1 = _lib.LAYER_SHORTCUT, 2, 0
+    descs = [conv_desc(128, 3, 1), conv_desc(64, 1, 1), conv_desc(128, 3, 1), sc]
+    monkeypatch.setenv("RTOD_TC_ROW", "1")
+    cfgs = []
+    outs = run_block(lib, descs, x, {0: w0, 1: w1, 2: w2}, _lib.PLAN_NO_AUTOTUNE, configs=cfgs)
+    assert [c["row"] for c in cfgs] == [1, 0, 1]
+    monkeypatch.setenv("RTOD_TC_ROW", "0")
+    cfgs = []
+    plain = run_block(lib, descs, x, {0: w0, 1: w1, 2: w2}, _lib.PLAN_NO_AUTOTUNE, configs=cfgs)
+    assert [c["row"] for c in cfgs] == [0, 0, 0]
+    tol = BLOCK_TOL["fp16"]
+    assert frac_within(outs[0], ref_block(x, w0, 3, 1, True, "fp16"), *tol) == 1.0
+    assert frac_within(outs[3], ref_block(outs[1], w2, 3, 1, True, "fp16") + outs[0], *tol) == 1.0
+    for a, b in zip(outs, plain):
+        assert torch.equal(a, b)
 
 
 def test_conv_block_two_term_weights_every_launch_configuration(lib, monkeypatch):
