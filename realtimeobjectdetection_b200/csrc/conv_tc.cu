@@ -43,7 +43,11 @@ namespace {
 
 constexpr int kFirstEpiWarp = 4;                // warps 0-3: TMA producer A, MMA issuer, TMA producer B, 2nd producer A
 constexpr int threads_for(int epi_warps, int subs = 1) { return 32 * (kFirstEpiWarp + epi_warps) * subs; }
-constexpr uint32_t kResidentLimit = 100 * 1024; // largest weight matrix kept resident in shared memory
+// largest weight matrix kept resident in shared memory (RTOD_TC_RESIDENT_KB: tuning knob)
+static uint32_t resident_limit() {
+    static const uint32_t v = getenv("RTOD_TC_RESIDENT_KB") ? (uint32_t)atoi(getenv("RTOD_TC_RESIDENT_KB")) * 1024u : 100u * 1024u;
+    return v;
+}
 constexpr uint32_t kResidentLimitRow = 150 * 1024;   // row mode (always resident; its stages are small slabs)
 constexpr int kSlabRows = kBM + 2;              // row mode: input pixels x0-1 .. x0+128 of one image row
 
@@ -559,14 +563,14 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
     // resident weights if that is what makes them fit; fat tiles (BN = 256) keep one CTA per SM,
     // eight epilogue warps and the deepest operand ring that fits.
     const uint32_t w_bytes = (uint32_t)(BN << a.w_split) * a.K * 2;
-    const bool may_reside = a.Cout_pad == BN && w_bytes <= (row ? kResidentLimitRow : kResidentLimit) &&
+    const bool may_reside = a.Cout_pad == BN && w_bytes <= (row ? kResidentLimitRow : resident_limit()) &&
                             (row || getenv("RTOD_TC_NO_RESIDENT") == nullptr);
     p.row_mode = row;
     p.slab_bytes = ((uint32_t)kSlabRows * BK * 2 + 1023u) & ~1023u;
     p.segs = (a.out.W + kBM - 1) / kBM;
     const uint32_t a_stage = row ? p.slab_bytes : (uint32_t)kBM * BK * 2;
     if (row && !may_reside) return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: row mode needs resident weights");
-    if (subs == 2 && (2 * cols > 512 || a.Cout_pad != BN || w_bytes > 2 * kResidentLimit || getenv("RTOD_TC_NO_RESIDENT")))
+    if (subs == 2 && (2 * cols > 512 || a.Cout_pad != BN || w_bytes > 2 * resident_limit() || getenv("RTOD_TC_NO_RESIDENT")))
         return fail(RTOD_ERR_UNSUPPORTED, "conv_tc: dual pipeline needs resident weights and 2 x %d TMEM columns", cols);
     int max_ctas = subs == 2 ? 1 : 512 / cols;
     if (const char* e = getenv("RTOD_TC_CTAS")) { const int v = atoi(e); if (v >= 1 && v < max_ctas) max_ctas = v; }
