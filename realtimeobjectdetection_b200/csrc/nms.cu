@@ -281,6 +281,128 @@ nms_scan_kernel(const float* __restrict__ pred, long long total_rows, int N, int
 }
 
 // =============================================================================================
+// kernel 1': the same scan without streaming the tensor.  Only the objectness column decides whether a row
+// matters (src/util.py:116-117 multiplies everything else by the mask), so every lane reads the 4 bytes of ONE row
+// (one 32-byte sector of the 340-byte row reaches the SM) and only the surviving rows -- ~1 % in a detector's
+// output -- are read in full, eight lanes per row.  DRAM traffic falls from B*N*(5+C)*4 bytes to about a fifth
+// (sector granularity); the result (candidate counts and keys, in any order: the image pass sorts them) is the same.
+// =============================================================================================
+constexpr int kSparseThreads = 256;
+constexpr int kSparseGroups = 4;                 // 32-row groups per warp iteration: four independent loads per lane
+
+__global__ void __launch_bounds__(kSparseThreads)
+nms_scan_sparse_kernel(const float* __restrict__ pred, long long total_rows, int N, int L, int C, float conf, int P,
+                       int* __restrict__ cand_count, unsigned long long* __restrict__ keys) {
+    const int lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // the image pass may be scheduled early
+    const long long warps_total = (long long)gridDim.x * (kSparseThreads / 32);
+    const long long n_blocks = (total_rows + 32 * kSparseGroups - 1) / (32 * kSparseGroups);
+    for (long long blk = (long long)blockIdx.x * (kSparseThreads / 32) + (threadIdx.x >> 5); blk < n_blocks; blk += warps_total) {
+        const long long base = blk * (32 * kSparseGroups);
+        float obj[kSparseGroups];
+#pragma unroll
+        for (int g = 0; g < kSparseGroups; ++g) {
+            const long long row = base + g * 32 + lane;
+            obj[g] = row < total_rows ? __ldg(pred + row * L + 4) : 0.0f;
+        }
+#pragma unroll
+        for (int g = 0; g < kSparseGroups; ++g) {
+            const long long r0 = base + g * 32;
+            // strict '>' in fp32, then "masked objectness != 0" (src/util.py:116-117, :275)
+            const bool keep = r0 + lane < total_rows && __fmul_rn(obj[g], obj[g] > conf ? 1.0f : 0.0f) != 0.0f;
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            if (mask == 0u) continue;
+            const int n_keep = __popc(mask);
+            // N >= 32: the group touches at most two images -> one atomicAdd per image reserves contiguous slots
+            const bool grouped = N >= 32;
+            long long img_a = 0;
+            int row_a0 = 0, split = 32, slot_a = 0, slot_b = 0, cnt_a = n_keep;
+            if (grouped) {
+                img_a = r0 / N;
+                row_a0 = (int)(r0 - img_a * N);
+                split = N - row_a0;                           // rows of image a in this group (may exceed 32)
+                const unsigned lo_mask = split >= 32 ? 0xffffffffu : ((1u << split) - 1u);
+                cnt_a = __popc(mask & lo_mask);
+                const int cnt_b = n_keep - cnt_a;
+                if (lane == 0) {
+                    slot_a = cnt_a ? atomicAdd(&cand_count[img_a], cnt_a) : 0;
+                    slot_b = cnt_b ? atomicAdd(&cand_count[img_a + 1], cnt_b) : 0;
+                }
+                slot_a = __shfl_sync(0xffffffffu, slot_a, 0);
+                slot_b = __shfl_sync(0xffffffffu, slot_b, 0);
+            }
+            // surviving rows, four at a time (8 lanes each): first-max class over the C scores (ties -> lowest index,
+            // NaN as torch.max), 64-bit sort key, append to the image's candidate list
+            for (int o0 = 0; o0 < n_keep; o0 += 4) {
+                const int ordinal = o0 + sub;
+                const bool have = ordinal < n_keep;
+                const int r = have ? (int)__fns(mask, 0, ordinal + 1) : 0;
+                const float o = __shfl_sync(0xffffffffu, obj[g], r);
+                const float* row = pred + (r0 + r) * L;
+                const float m = o > conf ? 1.0f : 0.0f;
+                float best = -INFINITY;
+                int best_idx = 0x7fffffff;
+                if (have)
+                    for (int j0 = l8; j0 < C; j0 += 32) {      // four independent loads, then the ordered compares
+                        float v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) v[u] = j0 + 8 * u < C ? __ldg(row + 5 + j0 + 8 * u) : 0.0f;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = j0 + 8 * u;
+                            if (j >= C) break;
+                            const float x = __fmul_rn(v[u], m);
+                            const bool take = (best_idx == 0x7fffffff) || (x > best) || (x != x && best == best);
+                            if (take) {
+                                best = x;
+                                best_idx = j;
+                            }
+                        }
+                    }
+#pragma unroll
+                for (int off = 4; off > 0; off >>= 1) {                  // stays inside the 8-lane group
+                    const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
+                    const bool a_nan = best != best, b_nan = ov != ov;
+                    bool other;
+                    if (oi == 0x7fffffff) other = false;
+                    else if (best_idx == 0x7fffffff) other = true;
+                    else if (a_nan || b_nan) other = (a_nan && b_nan) ? (oi < best_idx) : b_nan;
+                    else other = (ov > best) || (ov == best && oi < best_idx);
+                    if (other) {
+                        best = ov;
+                        best_idx = oi;
+                    }
+                }
+                if (have && l8 == 0) {
+                    long long img;
+                    int row_in_img, slot;
+                    if (grouped) {
+                        const bool in_a = r < split;
+                        img = in_a ? img_a : img_a + 1;
+                        row_in_img = in_a ? row_a0 + r : r - split;
+                        slot = in_a ? slot_a + ordinal : slot_b + ordinal - cnt_a;
+                    } else {
+                        const long long grow = r0 + r;
+                        img = grow / N;
+                        row_in_img = (int)(grow - img * N);
+                        slot = atomicAdd(&cand_count[img], 1);
+                    }
+                    unsigned long long key = kDeadKey;
+                    if (C > 0 && best != 0.0f) {                      // src/util.py:305 cls_conf != 0
+                        const float mobj = __fmul_rn(o, m);
+                        key = ((unsigned long long)best_idx << 52) |
+                              ((unsigned long long)(~orderable(mobj)) << 20) |
+                              (unsigned long long)row_in_img;
+                    }
+                    keys[img * (long long)P + slot] = key;
+                }
+            }
+        }
+    }
+}
+
+// =============================================================================================
 // kernel 2: per-image sort + per-class greedy suppression + ordered compaction
 // =============================================================================================
 __device__ __forceinline__ int upper_bound_class(const unsigned long long* keys, int lo, int hi,
@@ -303,9 +425,13 @@ nms_image_kernel(const float* __restrict__ pred, int N, int L, float conf, float
                  const int* __restrict__ cand_count, unsigned long long* __restrict__ keys_g,
                  uint32_t* __restrict__ klist_g, uint32_t* __restrict__ kbits_g,
                  uint32_t* __restrict__ kept_pair, int* __restrict__ kept_count, int smem_cap, int n_lo,
-                 int n_hi) {
+                 int n_hi, int box_cap, int B, int* __restrict__ kept_flag, float* __restrict__ out_rows, int out_cap,
+                 int* __restrict__ out_count, int* __restrict__ err_flag) {
+    // kept_flag != null ("resident" launch: one CTA per image, all of them co-resident): the emit step is fused --
+    // every CTA publishes its kept count (+1) in kept_flag[img], sums its predecessors' and writes its own rows
     extern __shared__ __align__(16) unsigned char image_smem[];
-    __shared__ int s_live, s_cursor, s_total;
+    __shared__ int s_live, s_cursor, s_total, s_offset;
+    __shared__ int s_part[kImageThreads / 32];
     __shared__ int s_warp_sums[kImageThreads / 32];
 
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -315,11 +441,12 @@ nms_image_kernel(const float* __restrict__ pred, int N, int L, float conf, float
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     int n = cand_count[img];
     if (n > N) n = N;
-    if (n <= 0) {
+    if (n <= 0 && !kept_flag) {
         if (n_lo < 0 && tid == 0) kept_count[img] = 0;     // the light pass owns the empty images
         return;
     }
-    if (n <= n_lo || n > n_hi) return;                       // the other pass handles this image
+    if (!kept_flag && (n <= n_lo || n > n_hi)) return;       // the other pass handles this image
+    if (n < 0) n = 0;
     int np = 32;
     while (np < n) np <<= 1;
 
@@ -364,11 +491,35 @@ nms_image_kernel(const float* __restrict__ pred, int N, int L, float conf, float
         if (keys[i] != kDeadKey && (i + 1 == np || keys[i + 1] == kDeadKey)) s_live = i + 1;
     __syncthreads();
     const int n_live = s_live;
+    const float* img_pred = pred + (long long)img * N * L;
+    // the candidates' corner boxes, gathered ONCE into shared memory (all lanes in parallel) when they fit: the
+    // suppression loops below then never wait on global memory
+    float* sbox = reinterpret_cast<float*>(image_smem + (size_t)smem_cap * 12 + (size_t)smem_cap / 8);
+    const bool staged = np <= smem_cap && n_live <= box_cap;
+    if (staged) {
+        for (int i = tid; i < n_live; i += nthreads) {
+            const Box b = load_box(img_pred + (long long)(keys[i] & 0xFFFFFull) * L, conf);
+            sbox[i] = b.x1;
+            sbox[box_cap + i] = b.y1;
+            sbox[2 * box_cap + i] = b.x2;
+            sbox[3 * box_cap + i] = b.y2;
+            sbox[4 * box_cap + i] = b.area;
+        }
+        __syncthreads();
+    }
+    auto box_at = [&](int pos) {
+        if (staged) {
+            Box b;
+            b.x1 = sbox[pos]; b.y1 = sbox[box_cap + pos]; b.x2 = sbox[2 * box_cap + pos]; b.y2 = sbox[3 * box_cap + pos];
+            b.area = sbox[4 * box_cap + pos];
+            return b;
+        }
+        return load_box(img_pred + (long long)(keys[pos] & 0xFFFFFull) * L, conf);
+    };
 
     // ---- greedy suppression: class c belongs to warp c % nwarps.  Each lane finds the segment of one of
     //      its warp's classes by binary search in the sorted keys (no claiming, no contention), then the
     //      warp walks through the non-empty segments one after the other.
-    const float* img_pred = pred + (long long)img * N * L;
     const int nwarps = nthreads >> 5;
     const int n_classes = L - 5;
     auto lower_bound_class = [&](unsigned long long cls) {     // first position with class field >= cls
@@ -399,15 +550,14 @@ nms_image_kernel(const float* __restrict__ pred, int N, int L, float conf, float
             const int p = t0 + lane;
             const bool valid = p < seg_hi;
             Box mine = {0.f, 0.f, 0.f, 0.f, 0.f};
-            if (valid) mine = load_box(img_pred + (long long)(keys[p] & 0xFFFFFull) * L, conf);
+            if (valid) mine = box_at(p);
             bool alive = valid;
 
             // boxes kept in earlier tiles of this class suppress first
             for (int base = 0; base < kept_in_seg; base += 32) {
                 Box kb = {0.f, 0.f, 0.f, 0.f, 0.f};
                 if (base + lane < kept_in_seg) {
-                    const uint32_t pos = klist[seg_lo + base + lane];
-                    kb = load_box(img_pred + (long long)(keys[pos] & 0xFFFFFull) * L, conf);
+                    kb = box_at((int)klist[seg_lo + base + lane]);
                 }
                 const int cnt = min(32, kept_in_seg - base);
                 for (int j = 0; j < cnt; ++j) {
@@ -491,6 +641,58 @@ nms_image_kernel(const float* __restrict__ pred, int N, int L, float conf, float
         __syncthreads();
     }
     if (tid == 0) kept_count[img] = running;
+    if (!kept_flag) return;
+
+    // ---- fused emit (src/util.py:332-341): publish the count, add up the predecessors', write the rows --------------
+    __syncthreads();                                       // kept_pair rows of this image are written
+    if (tid == 0) {
+        __threadfence();
+        atomicExch(&kept_flag[img], running + 1);
+    }
+    int acc = 0;
+    for (int i = tid; i < img; i += nthreads) {
+        int v = 0;
+        const unsigned long long t0 = global_timer_ns();
+        while ((v = *reinterpret_cast<volatile int*>(&kept_flag[i])) == 0) {
+            if (global_timer_ns() - t0 > 2000000000ull) {          // 2 s: report, do not hang
+                atomicExch(err_flag, 3);
+                v = 1;
+                break;
+            }
+        }
+        acc += v - 1;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) s_part[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        int total = 0;
+        for (int i = 0; i < (nthreads >> 5); ++i) total += s_part[i];
+        s_offset = total;
+        // a pipeline time-out anywhere in this call turns the count negative: the host raises (util.py)
+        if (img == B - 1) *out_count = *reinterpret_cast<volatile int*>(err_flag) ? -1 : total + running;
+    }
+    __syncthreads();
+    const int offset = s_offset;
+    for (int k = tid; k < running; k += nthreads) {
+        const long long dst = (long long)offset + k;
+        if (dst >= out_cap) break;
+        const uint32_t pair = kept_pair[(long long)img * N + k];
+        const int row = (int)(pair & 0xFFFFFu), cls = (int)(pair >> 20);
+        const float* src = img_pred + (long long)row * L;
+        const Box b = load_box(src, conf);
+        const float m = src[4] > conf ? 1.0f : 0.0f;
+        float* o = out_rows + dst * 8;
+        o[0] = (float)img;
+        o[1] = b.x1;
+        o[2] = b.y1;
+        o[3] = b.x2;
+        o[4] = b.y2;
+        o[5] = __fmul_rn(src[4], m);
+        o[6] = __fmul_rn(src[5 + cls], m);
+        o[7] = (float)cls;
+    }
 }
 
 // =============================================================================================
@@ -499,7 +701,7 @@ nms_image_kernel(const float* __restrict__ pred, int N, int L, float conf, float
 __global__ void __launch_bounds__(256)
 nms_emit_kernel(const float* __restrict__ pred, int B, int N, int L, float conf,
                 const uint32_t* __restrict__ kept_pair, const int* __restrict__ kept_count,
-                float* __restrict__ out_rows, int cap, int* __restrict__ out_count) {
+                float* __restrict__ out_rows, int cap, int* __restrict__ out_count, const int* __restrict__ err_flag) {
     __shared__ int s_part[8];
     __shared__ int s_offset;
     const int img = blockIdx.x, tid = threadIdx.x;
@@ -514,7 +716,7 @@ nms_emit_kernel(const float* __restrict__ pred, int B, int N, int L, float conf,
         int total = 0;
         for (int i = 0; i < 8; ++i) total += s_part[i];
         s_offset = total;
-        if (img == B - 1) *out_count = total + kept_count[img];
+        if (img == B - 1) *out_count = *reinterpret_cast<const volatile int*>(err_flag) ? -1 : total + kept_count[img];
     }
     __syncthreads();
     const int offset = s_offset, mine = kept_count[img];
@@ -569,7 +771,7 @@ int pow2_ceil(int v) {
 }
 
 struct NmsLayout {
-    size_t off_cand, off_kept, off_err, off_keys, off_pair, off_klist, off_kbits, total;
+    size_t off_cand, off_kept, off_err, off_flag, off_keys, off_pair, off_klist, off_kbits, total;
     int P;
 };
 
@@ -580,6 +782,7 @@ NmsLayout nms_layout(int B, int N) {
     l.off_cand = o;  o = align_up(o + sizeof(int) * (size_t)B, 256);
     l.off_kept = o;  o = align_up(o + sizeof(int) * (size_t)B, 256);
     l.off_err = o;   o = align_up(o + sizeof(int), 256);
+    l.off_flag = o;  o = align_up(o + sizeof(int) * (size_t)B, 256);
     l.off_keys = o;  o = align_up(o + 8ull * B * l.P, 256);
     l.off_pair = o;  o = align_up(o + 4ull * B * (size_t)(N > 0 ? N : 1), 256);
     l.off_klist = o; l.off_kbits = o;
@@ -631,81 +834,99 @@ extern "C" int rtod_write_results(const float* pred, int B, int N, int C, float 
     int* cand_count = reinterpret_cast<int*>(ws + lay.off_cand);
     int* kept_count = reinterpret_cast<int*>(ws + lay.off_kept);
     int* err_flag = reinterpret_cast<int*>(ws + lay.off_err);
+    int* kept_flag = reinterpret_cast<int*>(ws + lay.off_flag);
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + lay.off_keys);
     uint32_t* pair = reinterpret_cast<uint32_t*>(ws + lay.off_pair);
     uint32_t* klist = reinterpret_cast<uint32_t*>(ws + lay.off_klist);
     uint32_t* kbits = reinterpret_cast<uint32_t*>(ws + lay.off_kbits);
     const int L = 5 + C;
 
-    // counters (cand, kept, err) are contiguous at the start of the workspace
+    // counters (cand, kept, err, flags) are contiguous at the start of the workspace
     RTOD_CUDA_OK(cudaMemsetAsync(ws, 0, lay.off_keys, stream));
 
     // ---- scan -----------------------------------------------------------------------------
-    int rows_per_chunk = kScanStageBytes / (L * 4);
-    if (rows_per_chunk > kScanMaxRows) rows_per_chunk = kScanMaxRows;
-    if (rows_per_chunk >= 4) rows_per_chunk &= ~3;
-    if (rows_per_chunk < 1) rows_per_chunk = 1;
-    int use_bulk = ((reinterpret_cast<uintptr_t>(pred) & 15u) == 0) &&
-                         (((long long)rows_per_chunk * L) % 4 == 0);
-    if (const char* e = getenv("RTOD_NMS_DBG")) use_bulk |= atoi(e) << 1;
-    const size_t stage_bytes = (size_t)(((rows_per_chunk * L + 31) / 32) * 32) * 4;
-    const size_t scan_smem = kScanStages * stage_bytes;
-    // per device (a process may drive several GPUs) and cheap: set on every call
-    RTOD_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kScanStages * (kScanStageBytes + 128)));
     const long long total_rows = (long long)B * N;
-    const long long n_chunks = (total_rows + rows_per_chunk - 1) / rows_per_chunk;
-    int per_sm = (int)(200 * 1024 / (scan_smem + 1024));
-    if (per_sm > 8) per_sm = 8;
-    if (per_sm < 1) per_sm = 1;
-    long long grid = (long long)kNumSMs * per_sm;
-    if (grid > n_chunks) grid = n_chunks;
-    nms_scan_kernel<<<(unsigned)grid, kScanThreads, scan_smem, stream>>>(
-        pred, total_rows, N, L, C, confidence, lay.P, rows_per_chunk, use_bulk, cand_count, keys,
-        err_flag);
-    RTOD_LAUNCH_OK("nms_scan_kernel");
+    static const bool stream_scan = getenv("RTOD_NMS_STREAM") != nullptr;     // the tensor-streaming scan (comparison runs)
+    if (!stream_scan) {
+        const long long n_blocks = (total_rows + 32 * kSparseGroups - 1) / (32 * kSparseGroups);
+        long long grid = (n_blocks + kSparseThreads / 32 - 1) / (kSparseThreads / 32);
+        if (grid > (long long)kNumSMs * 8) grid = (long long)kNumSMs * 8;
+        nms_scan_sparse_kernel<<<(unsigned)grid, kSparseThreads, 0, stream>>>(pred, total_rows, N, L, C, confidence, lay.P,
+                                                                            cand_count, keys);
+        RTOD_LAUNCH_OK("nms_scan_sparse_kernel");
+    } else {
+        int rows_per_chunk = kScanStageBytes / (L * 4);
+        if (rows_per_chunk > kScanMaxRows) rows_per_chunk = kScanMaxRows;
+        if (rows_per_chunk >= 4) rows_per_chunk &= ~3;
+        if (rows_per_chunk < 1) rows_per_chunk = 1;
+        int use_bulk = ((reinterpret_cast<uintptr_t>(pred) & 15u) == 0) &&
+                             (((long long)rows_per_chunk * L) % 4 == 0);
+        if (const char* e = getenv("RTOD_NMS_DBG")) use_bulk |= atoi(e) << 1;
+        const size_t stage_bytes = (size_t)(((rows_per_chunk * L + 31) / 32) * 32) * 4;
+        const size_t scan_smem = kScanStages * stage_bytes;
+        // per device (a process may drive several GPUs) and cheap: set on every call
+        RTOD_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kScanStages * (kScanStageBytes + 128)));
+        const long long n_chunks = (total_rows + rows_per_chunk - 1) / rows_per_chunk;
+        int per_sm = (int)(200 * 1024 / (scan_smem + 1024));
+        if (per_sm > 8) per_sm = 8;
+        if (per_sm < 1) per_sm = 1;
+        long long grid = (long long)kNumSMs * per_sm;
+        if (grid > n_chunks) grid = n_chunks;
+        nms_scan_kernel<<<(unsigned)grid, kScanThreads, scan_smem, stream>>>(
+            pred, total_rows, N, L, C, confidence, lay.P, rows_per_chunk, use_bulk, cand_count, keys,
+            err_flag);
+        RTOD_LAUNCH_OK("nms_scan_kernel");
+    }
 
-    // ---- per-image sort + suppression ---------------------------------------------------
+    // ---- per-image sort + suppression (+ emit) ---------------------------------------------
+    constexpr int kBoxCap = 1024;                            // candidates per image whose boxes are staged in shared memory
     RTOD_CUDA_OK(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kSortSmemCap * 12 + kSortSmemCap / 8));
-    {   // light pass: images with at most kLightCap candidates (and the empty ones)
-        const int cap = lay.P < kLightCap ? lay.P : kLightCap;
-        cudaLaunchAttribute pdl[1];
-        pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        pdl[0].val.programmaticStreamSerializationAllowed = 1;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)B, 1, 1);
-        cfg.blockDim = dim3(512, 1, 1);
-        cfg.dynamicSmemBytes = (size_t)cap * 12 + cap / 8;
-        cfg.stream = stream;
-        cfg.attrs = pdl;
-        cfg.numAttrs = 1;
+                                      kSortSmemCap * 12 + kSortSmemCap / 8 + kBoxCap * 20));
+    cudaLaunchAttribute pdl[1];
+    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)B, 1, 1);
+    cfg.stream = stream;
+    cfg.attrs = pdl;
+    cfg.numAttrs = 1;
+    static const bool no_fused = getenv("RTOD_NMS_NO_FUSED_EMIT") != nullptr;
+    if (B <= kNumSMs && !no_fused) {
+        // resident launch: one CTA per image and SM, every image size in one configuration, emit fused (the CTAs wait
+        // for their predecessors' counts, which needs all of them on the machine at once)
+        const int hcap = lay.P < kSortSmemCap ? lay.P : kSortSmemCap;
+        static const int threads = getenv("RTOD_NMS_THREADS") ? atoi(getenv("RTOD_NMS_THREADS")) : kImageThreads;
+        cfg.blockDim = dim3((unsigned)(threads >= 128 && threads <= kImageThreads && threads % 32 == 0 ? threads : kImageThreads), 1, 1);
+        cfg.dynamicSmemBytes = (size_t)hcap * 12 + hcap / 8 + kBoxCap * 20;
         RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, nms_image_kernel, pred, N, L, confidence, nms_conf, lay.P,
-                                        (const int*)cand_count, keys, klist, kbits, pair, kept_count, cap, -1, cap));
+                                        (const int*)cand_count, keys, klist, kbits, pair, kept_count, hcap, -1, 0x7fffffff,
+                                        (int)kBoxCap, B, kept_flag, out_rows, cap, out_count, err_flag));
+        return RTOD_OK;
+    }
+    {   // light pass: images with at most kLightCap candidates (and the empty ones)
+        const int lcap = lay.P < kLightCap ? lay.P : kLightCap;
+        cfg.blockDim = dim3(512, 1, 1);
+        cfg.dynamicSmemBytes = (size_t)lcap * 12 + lcap / 8 + kBoxCap * 20;
+        RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, nms_image_kernel, pred, N, L, confidence, nms_conf, lay.P,
+                                        (const int*)cand_count, keys, klist, kbits, pair, kept_count, lcap, -1, lcap,
+                                        (int)kBoxCap, B, (int*)nullptr, (float*)nullptr, 0, (int*)nullptr, err_flag));
         if (lay.P > kLightCap) {   // heavy pass: dense images
             const int hcap = lay.P < kSortSmemCap ? lay.P : kSortSmemCap;
             cfg.blockDim = dim3(kImageThreads, 1, 1);
-            cfg.dynamicSmemBytes = (size_t)hcap * 12 + hcap / 8;
+            cfg.dynamicSmemBytes = (size_t)hcap * 12 + hcap / 8 + kBoxCap * 20;
             RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, nms_image_kernel, pred, N, L, confidence, nms_conf, lay.P,
                                             (const int*)cand_count, keys, klist, kbits, pair, kept_count, hcap,
-                                            (int)kLightCap, 0x7fffffff));
+                                            (int)kLightCap, 0x7fffffff, (int)kBoxCap, B, (int*)nullptr, (float*)nullptr, 0,
+                                            (int*)nullptr, err_flag));
         }
     }
 
     // ---- emit ---------------------------------------------------------------------------------
-    {
-        cudaLaunchAttribute pdl[1];
-        pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        pdl[0].val.programmaticStreamSerializationAllowed = 1;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)B, 1, 1);
-        cfg.blockDim = dim3(256, 1, 1);
-        cfg.stream = stream;
-        cfg.attrs = pdl;
-        cfg.numAttrs = 1;
-        RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, nms_emit_kernel, pred, B, N, L, confidence, (const uint32_t*)pair,
-                                        (const int*)kept_count, out_rows, cap, out_count));
-    }
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, nms_emit_kernel, pred, B, N, L, confidence, (const uint32_t*)pair,
+                                    (const int*)kept_count, out_rows, cap, out_count, (const int*)err_flag));
     return RTOD_OK;
 }
 

@@ -138,6 +138,8 @@ class PendingDetections:
                 _PINNED_COUNTS.append(self._count_host)        # recycled: no host allocation per call
             self._count_host = None
         d = self._d
+        if d < 0:
+            raise RuntimeError("write_results: device-side failure (a bounded wait in the NMS kernels timed out)")
         if d == 0:
             return 0
         if d > self._cap:

@@ -290,7 +290,7 @@ def stage_nmsbench():
     (CUDA events), plus the decode microbench on [256, 255, G, G] heads."""
     import ctypes
     lib = _lib.load()
-    B, N, C = 256, 10647, 80
+    B, N, C = int(os.environ.get("NMSBENCH_B", "256")), 10647, 80
     nbytes = lib.rtod_write_results_workspace_bytes(B, N, C)
     ws = torch.empty(nbytes + 256, dtype=torch.uint8, device="cuda")
     ws_ptr = (ws.data_ptr() + 255) // 256 * 256
@@ -310,8 +310,8 @@ def stage_nmsbench():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 20
-        print("write_results [256,10647,85] density %.2f clustered %d: %.1f us -> %.0f GB/s (%.2f of 6552.6), %d detections"
-              % (dens, clustered, ms * 1e3, pred.numel() * 4 / ms / 1e6, pred.numel() * 4 / ms / 1e6 / 6552.6, int(count.item())))
+        print("write_results [%d,10647,85] density %.2f clustered %d: %.1f us -> %.0f GB/s (%.2f of 6552.6), %d detections"
+              % (B, dens, clustered, ms * 1e3, pred.numel() * 4 / ms / 1e6, pred.numel() * 4 / ms / 1e6 / 6552.6, int(count.item())))
         del pred
     anchors = (ctypes.c_float * 6)(116, 90, 156, 198, 373, 326)
     for G in (13, 26, 52):
