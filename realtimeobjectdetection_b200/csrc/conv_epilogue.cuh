@@ -32,7 +32,10 @@ static __device__ __forceinline__ uint32_t acc_column(const ConvTcParams& p, int
 // release(buf): arrive on the accumulator-empty barrier the MMA issuer waits on (called by one lane)
 // The TMA / bulk-group / mbarrier-arrive instructions of a warp are always issued by its elect.sync lane
 // (deterministic for a full mask), so the per-thread bulk async-groups stay with one thread.
-template <int kEpiWarps, bool kF16, class Origin, class Release>
+// kAhead: registers to spare (one CTA per SM): the folded bias of a 32-column group is loaded BEFORE the accumulator
+// read is awaited and both terms of a two-term accumulator are read with one wait -- the epilogue of a thin tile is a
+// single warp's dependent chain (measured ~1100 cycles per 32 columns), every round trip taken out of it counts
+template <int kEpiWarps, bool kF16, bool kAhead, class Origin, class Release>
 static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint32_t tmem_base, uint64_t* acc_full,
                                                      uint8_t* epi_stage, uint64_t* res_bar, int ew, int lane,
                                                      int tile_first, int tile_step, Origin origin, Release release) {
@@ -60,11 +63,19 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
     // drains quickly and the host sees the flag.
     uint32_t g = 0;                                      // chunks this warp has handled
     int local = 0;
+    TRACE_DECL(t_acc);
+    TRACE_DECL(t_slice);
+    TRACE_DECL(t_tmem);
+    TRACE_DECL(t_math);
+    TRACE_DECL(t_store);
+    TRACE_T0(t_begin);
     for (int tile = tile_first; tile < p.total_tiles; tile += tile_step, ++local) {
         const int buf = local & 1;
         int m0, n0, row;
         origin(tile, m0, n0, row);
+        TRACE_T0(ta);
         mbar_wait(&acc_full[buf], (uint32_t)(local >> 1) & 1u, p.err_flag);
+        TRACE_ADD(t_acc, ta);
         tc_fence_after();
         if (cg >= n_chunks) {                            // tile narrower than the column groups: nothing to do
             if (elect_one()) release(buf);
@@ -74,6 +85,7 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
         for (int c = cg; c < n_chunks; c += kColGroups, ++g) {
             const uint32_t sb = sbufs == 2 ? (g & 1u) : 0u;
             uint8_t* slice = my_stage + sb * kEpiSlice;
+            TRACE_T0(ts);
             if (!p.has_res) {                            // the store that last read this slice has drained
                 if (elect_one()) {
                     if (sbufs == 2) bulk_wait_read_1();
@@ -81,12 +93,29 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
                 }
                 __syncwarp();
             }
+            TRACE_ADD(t_slice, ts);
             for (int h = 0; h < halves; ++h) {
                 uint32_t v[32];
+                TRACE_T0(tt);
+                const int nbase = n0 + c * ecols + h * 32;
+                float4 bq[kAhead ? 8 : 1];
+                if (kAhead) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) bq[q] = __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + q);
+                }
                 if (!(p.dbg & 32)) {
                     const uint32_t col = acc_column(p, c * ecols + h * 32);
-                    tmem_ld_32x32(tmem_acc + col, v);
-                    if (p.w_cat) tmem_ld_add_32x32(tmem_acc + col + (uint32_t)p.lo_col, v);      // hi + lo term
+                    if (kAhead && p.w_cat) {                 // hi + lo term, one wait
+                        uint32_t w[32];
+                        tmem_ld_32x32_issue(tmem_acc + col, v);
+                        tmem_ld_32x32_issue(tmem_acc + col + (uint32_t)p.lo_col, w);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+                    } else {
+                        tmem_ld_32x32(tmem_acc + col, v);
+                        if (p.w_cat) tmem_ld_add_32x32(tmem_acc + col + (uint32_t)p.lo_col, v);      // hi + lo term
+                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = (uint32_t)(j + lane);
@@ -97,13 +126,14 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
                     __syncwarp();
                     if (elect_one()) release(buf);
                 }
+                TRACE_ADD(t_tmem, tt);
+                TRACE_T0(tm);
                 if (p.has_res && h == 0)                 // shortcut operand of this chunk has landed in `slice`
                     mbar_wait(&my_res[sb], (sbufs == 2 ? (g >> 1) : g) & 1u, p.err_flag);
-                const int nbase = n0 + c * ecols + h * 32;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + q * 8));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + q * 8 + 4));
+                    const float4 b0 = kAhead ? bq[kAhead ? 2 * q : 0] : __ldg(reinterpret_cast<const float4*>(p.bias + nbase + q * 8));
+                    const float4 b1 = kAhead ? bq[kAhead ? 2 * q + 1 : 0] : __ldg(reinterpret_cast<const float4*>(p.bias + nbase + q * 8 + 4));
                     float f[8];
                     f[0] = __uint_as_float(v[q * 8 + 0]) + b0.x;
                     f[1] = __uint_as_float(v[q * 8 + 1]) + b0.y;
@@ -139,7 +169,9 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
                         *reinterpret_cast<uint4*>(slice + off) = o;
                     }
                 }
+                TRACE_ADD(t_math, tm);
             }
+            TRACE_T0(tst);
             fence_async_smem();                          // generic-proxy writes -> visible to the TMA
             __syncwarp();
             if (elect_one()) {
@@ -159,8 +191,14 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
                     }
                 }
             }
+            TRACE_ADD(t_store, tst);
         }
     }
+#ifdef RTOD_TC_TRACE
+    if ((p.dbg & 64) && blockIdx.x == 0 && ew == 0 && lane == 0)
+        printf("  epilogue warp 0: total %lld clk for %d tiles (%u chunks): acc_full wait %lld, slice wait %lld, tmem ld %lld, "
+               "math+res+st.shared %lld, fence+store+res issue %lld\n", clock64() - t_begin, local, g, t_acc, t_slice, t_tmem, t_math, t_store);
+#endif
     // shared memory must stay valid until the last stores have READ it; their global writes are complete and
     // visible at kernel completion, which is what the next layer (stream order / griddepcontrol.wait) waits for
     if (elect_one()) bulk_wait_read_0();

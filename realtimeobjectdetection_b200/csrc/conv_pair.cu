@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
         }
     } else {
         // ================= epilogue (conv_epilogue.cuh): each CTA stores its own 128 rows =================
-        conv_epilogue<kEpilogueWarps, kF16>(
+        conv_epilogue<kEpilogueWarps, kF16, true>(
             p, tmem_base, acc_full, epi_stage, res_full, warp - 2, lane, tile_first, tile_step,
             [&](int tile, int& m0, int& n0, int& row) {
                 const int n_tile = (int)fast_div((uint32_t)tile, p.fd_mtiles);

@@ -218,6 +218,26 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
                     ow = (m0 - prow * p.Wo) * p.stride - p.pad;
                     oh = (prow - on * p.Ho) * p.stride - p.pad;
                 }
+                if (p.a_prefetch && me == 0 && p.split_k == 1) {
+                    // pull the activation tile this CTA will need `a_prefetch` tiles from now into L2 (same N tile rows are
+                    // re-used by the other N tiles, so only for the first one)
+                    const int ft = tile + p.a_prefetch * item_step;
+                    const int fn = (int)fast_div((uint32_t)ft, p.fd_mtiles);
+                    if (ft < p.total_tiles && (fn == 0 || p.ks == 1)) {
+                        const int fm0 = (ft - fn * p.m_tiles) * kBM;
+                        if (p.ks == 1) {
+                            for (int c0 = 0; c0 < cin; c0 += p.BK) tma_prefetch_2d(&p.tmA, c0, fm0);
+                        } else {
+                            const int frow = (int)fast_div((uint32_t)fm0, p.fd_wo);
+                            const int fon = (int)fast_div((uint32_t)fm0, p.fd_howo);
+                            const int fow = (fm0 - frow * p.Wo) * p.stride - p.pad, foh = (frow - fon * p.Ho) * p.stride - p.pad;
+                            // the nine taps overlap almost completely: the centre row of taps touches every line once more
+                            for (int ky = 0; ky < p.ks; ++ky)
+                                for (int c0 = 0; c0 < cin; c0 += p.BK)
+                                    tma_prefetch_im2col_4d(&p.tmA, c0, fow, foh, fon, (uint16_t)1, (uint16_t)ky);
+                        }
+                    }
+                }
                 // taps outer, channel slices inner: all coordinates advance by additions (a lone thread retires
                 // one dependent instruction every ~5 cycles; one integer divide costs ~150)
                 for (int ky = 0; ok && ky < p.ks; ++ky)
@@ -415,7 +435,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
                 },
                 origin, release);
         else
-            conv_epilogue<kEpiWarps, kF16>(p, tmem_base, acc_full, epi_stage, res_full, warp - kFirstEpiWarp, lane,
+            conv_epilogue<kEpiWarps, kF16, (kEpiWarps == 8 || kSubs == 2)>(p, tmem_base, acc_full, epi_stage, res_full, warp - kFirstEpiWarp, lane,
                                      first_item, item_step, origin, release);
     }
 
@@ -545,6 +565,7 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
     p.w_cat = a.w_split ? 1 : 0;
     p.acc_cols = BN << p.w_cat;
     p.lo_col = BN;
+    p.a_prefetch = getenv("RTOD_TC_APF") ? atoi(getenv("RTOD_TC_APF")) : 0;
     // dual pipeline (two warp sets sharing resident weights in one CTA per SM): asked for by the autotuner / tests
     // through `force`, or by the heuristic for resident-weight layers whose weights are too large for two CTAs
     int subs = force ? (force->subs == 2 ? 2 : 1) : 1;

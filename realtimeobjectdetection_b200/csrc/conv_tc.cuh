@@ -45,6 +45,8 @@ struct alignas(64) ConvTcParams {
     int row_mode, segs;         // segs = ceil(Wo / 128) segments per image row
     uint32_t slab_bytes;        // one staged slab: 130 rows, rounded up to 1024
     uint32_t fd_segs[3], fd_ho[3];
+    int a_prefetch;             // activation tiles prefetched into L2 this many of the CTA's tiles ahead (0 = off): layers that
+                                // stream their input from HBM are bound by latency x bytes in flight, and the ring is small
     int lo_col;                 // column distance from a value's hi term to its lo term (w_cat): BN, pair kernel BN / 2
     int split_k, split_shift;   // K slices per output tile (power of two, 1 = off) and log2 of it
     float* split_scratch;       // [total_tiles][split_k][128][BN] fp32 partial accumulators

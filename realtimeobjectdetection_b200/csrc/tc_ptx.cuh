@@ -114,6 +114,17 @@ static __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUten
         "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
         : "memory");
 }
+// fire-and-forget L2 prefetch of one box of a tensor map (same coordinates as the load that will follow): raises the
+// bytes in flight beyond what the shared-memory ring can hold
+static __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+static __device__ __forceinline__ void tma_prefetch_im2col_4d(const CUtensorMap* map, int c, int w, int h, int n, uint16_t off_w,
+                                                              uint16_t off_h) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.im2col [%0, {%1, %2, %3, %4}], {%5, %6};" ::"l"(map), "r"(c), "r"(w),
+                 "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+                 : "memory");
+}
 // fire-and-forget L2 prefetch of a contiguous range (16-byte aligned, size a multiple of 16)
 static __device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
@@ -187,6 +198,21 @@ static __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+// the two halves of tmem_ld_32x32: issue (no wait) and wait -- several loads may be in flight before one wait
+static __device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+static __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // v[j] += TMEM[lane][col + j], j < 32, in two 16-column loads (keeps the register peak low): the second term of
 // a two-term-weight accumulator (columns [N, 2N) of the concatenated MMA) is folded into the first
