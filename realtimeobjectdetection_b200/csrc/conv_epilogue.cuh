@@ -35,20 +35,29 @@ static __device__ __forceinline__ uint32_t acc_column(const ConvTcParams& p, int
 // kAhead: registers to spare (one CTA per SM): the folded bias of a 32-column group is loaded BEFORE the accumulator
 // read is awaited and both terms of a two-term accumulator are read with one wait -- the epilogue of a thin tile is a
 // single warp's dependent chain (measured ~1100 cycles per 32 columns), every round trip taken out of it counts
-template <int kEpiWarps, bool kF16, bool kAhead, class Origin, class Release>
-static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint32_t tmem_base, uint64_t* acc_full,
+// kMode: -1 = every layer flag read from `p` at run time (rare combinations, bring-up switches); otherwise the flags
+// are compile-time constants (bit 0 leaky, bit 1 shortcut operand, bit 2 two-term accumulator, bit 3 fp32 head logits)
+// and the loop body is straight-line code: the generic body spends most of its issue slots on uniform branches and
+// instruction-cache misses (ncu source view of a 1x1 layer: stall_branch_resolving / stall_no_inst dominate)
+template <int kEpiWarps, bool kF16, bool kAhead, int kMode, class Origin, class Release>
+static __device__ __forceinline__ void conv_epilogue_body(const ConvTcParams& p, uint32_t tmem_base, uint64_t* acc_full,
                                                      uint8_t* epi_stage, uint64_t* res_bar, int ew, int lane,
                                                      int tile_first, int tile_step, Origin origin, Release release) {
     constexpr int kColGroups = kEpiWarps / 4;
+    const bool f_leaky = kMode < 0 ? p.leaky != 0 : (kMode & 1) != 0;
+    const bool f_res = kMode < 0 ? p.has_res != 0 : (kMode & 2) != 0;
+    const bool f_cat = kMode < 0 ? p.w_cat != 0 : (kMode & 4) != 0;
+    const bool f_fp32 = kMode < 0 ? p.out_fp32 != 0 : (kMode & 8) != 0;
+    const int f_dbg = kMode < 0 ? p.dbg : 0;
     const int quarter = (int)(threadIdx.x >> 5) & 3;     // TMEM lanes [32*quarter, +32) = rows of the tile
     const int cg = ew >> 2;                              // this warp's chunks: cg, cg + kColGroups, ...
     const int ecols = p.ecols;
-    const uint32_t erow = (uint32_t)ecols * (p.out_fp32 ? 4u : 2u);
+    const uint32_t erow = (uint32_t)ecols * (f_fp32 ? 4u : 2u);
     const int n_chunks = p.BN / ecols;
     const uint32_t sbufs = (uint32_t)p.stage_bufs;
     uint8_t* my_stage = epi_stage + (size_t)ew * sbufs * kEpiSlice;
     uint64_t* my_res = res_bar + ew * 2;
-    const int halves = p.out_fp32 ? 1 : (ecols + 31) / 32;              // 32 accumulator columns each
+    const int halves = f_fp32 ? 1 : (ecols + 31) / 32;              // 32 accumulator columns each
 
     auto issue_res = [&](int tile, int c, uint32_t sb) {                 // elected lane only
         int m0, n0, row;
@@ -57,7 +66,7 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
         if (p.row_mode) tma_load_3d(my_stage + sb * kEpiSlice, &p.tmRes, &my_res[sb], n0 + c * ecols, m0 + quarter * 32, row);
         else tma_load_2d(my_stage + sb * kEpiSlice, &p.tmRes, &my_res[sb], n0 + c * ecols, m0 + quarter * 32);
     };
-    if (p.has_res && cg < n_chunks && tile_first < p.total_tiles && elect_one()) issue_res(tile_first, cg, 0u);
+    if (f_res && cg < n_chunks && tile_first < p.total_tiles && elect_one()) issue_res(tile_first, cg, 0u);
 
     // NOTE: no early exit: after a time-out (*err_flag != 0) every wait returns at once, the loop
     // drains quickly and the host sees the flag.
@@ -86,7 +95,7 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
             const uint32_t sb = sbufs == 2 ? (g & 1u) : 0u;
             uint8_t* slice = my_stage + sb * kEpiSlice;
             TRACE_T0(ts);
-            if (!p.has_res) {                            // the store that last read this slice has drained
+            if (!f_res) {                            // the store that last read this slice has drained
                 if (elect_one()) {
                     if (sbufs == 2) bulk_wait_read_1();
                     else bulk_wait_read_0();
@@ -103,9 +112,9 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
 #pragma unroll
                     for (int q = 0; q < 8; ++q) bq[q] = __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + q);
                 }
-                if (!(p.dbg & 32)) {
-                    const uint32_t col = acc_column(p, c * ecols + h * 32);
-                    if (kAhead && p.w_cat) {                 // hi + lo term, one wait
+                if (!(f_dbg & 32)) {
+                    const uint32_t col = f_cat ? acc_column(p, c * ecols + h * 32) : (uint32_t)(c * ecols + h * 32);
+                    if (kAhead && f_cat) {                 // hi + lo term, one wait
                         uint32_t w[32];
                         tmem_ld_32x32_issue(tmem_acc + col, v);
                         tmem_ld_32x32_issue(tmem_acc + col + (uint32_t)p.lo_col, w);
@@ -114,7 +123,7 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
                         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
                     } else {
                         tmem_ld_32x32(tmem_acc + col, v);
-                        if (p.w_cat) tmem_ld_add_32x32(tmem_acc + col + (uint32_t)p.lo_col, v);      // hi + lo term
+                        if (f_cat) tmem_ld_add_32x32(tmem_acc + col + (uint32_t)p.lo_col, v);      // hi + lo term
                     }
                 } else {
 #pragma unroll
@@ -128,7 +137,7 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
                 }
                 TRACE_ADD(t_tmem, tt);
                 TRACE_T0(tm);
-                if (p.has_res && h == 0)                 // shortcut operand of this chunk has landed in `slice`
+                if (f_res && h == 0)                 // shortcut operand of this chunk has landed in `slice`
                     mbar_wait(&my_res[sb], (sbufs == 2 ? (g >> 1) : g) & 1u, p.err_flag);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -143,18 +152,18 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
                     f[5] = __uint_as_float(v[q * 8 + 5]) + b1.y;
                     f[6] = __uint_as_float(v[q * 8 + 6]) + b1.z;
                     f[7] = __uint_as_float(v[q * 8 + 7]) + b1.w;
-                    if (p.leaky) {
+                    if (f_leaky) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) f[j] = leaky01(f[j]);
                     }
-                    if (p.out_fp32) {                    // 8 fp32 = two 16-byte chunks
+                    if (f_fp32) {                    // 8 fp32 = two 16-byte chunks
                         *reinterpret_cast<float4*>(slice + staged_offset(lane, q * 2, erow)) =
                             make_float4(f[0], f[1], f[2], f[3]);
                         *reinterpret_cast<float4*>(slice + staged_offset(lane, q * 2 + 1, erow)) =
                             make_float4(f[4], f[5], f[6], f[7]);
                     } else {
                         const uint32_t off = staged_offset(lane, h * 4 + q, erow);
-                        if (p.has_res) {
+                        if (f_res) {
                             const uint4 r = *reinterpret_cast<const uint4*>(slice + off);
                             f[0] += h2_lo<kF16>(r.x); f[1] += h2_hi<kF16>(r.x);
                             f[2] += h2_lo<kF16>(r.y); f[3] += h2_hi<kF16>(r.y);
@@ -176,9 +185,9 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
             __syncwarp();
             if (elect_one()) {
                 if (p.row_mode) tma_store_3d(&p.tmOut, slice, n0 + c * ecols, m0 + quarter * 32, row);
-                else if (!(p.dbg & 16)) tma_store_2d(&p.tmOut, slice, n0 + c * ecols, m0 + quarter * 32);
+                else if (!(f_dbg & 16)) tma_store_2d(&p.tmOut, slice, n0 + c * ecols, m0 + quarter * 32);
                 bulk_commit();
-                if (p.has_res) {                         // shortcut operand of this warp's next chunk
+                if (f_res) {                         // shortcut operand of this warp's next chunk
                     int nt = tile, nc = c + kColGroups;
                     if (nc >= n_chunks) {
                         nt += tile_step;
@@ -195,7 +204,7 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
         }
     }
 #ifdef RTOD_TC_TRACE
-    if ((p.dbg & 64) && blockIdx.x == 0 && ew == 0 && lane == 0)
+    if ((f_dbg & 64) && blockIdx.x == 0 && ew == 0 && lane == 0)
         printf("  epilogue warp 0: total %lld clk for %d tiles (%u chunks): acc_full wait %lld, slice wait %lld, tmem ld %lld, "
                "math+res+st.shared %lld, fence+store+res issue %lld\n", clock64() - t_begin, local, g, t_acc, t_slice, t_tmem, t_math, t_store);
 #endif
@@ -203,6 +212,29 @@ static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint
     // visible at kernel completion, which is what the next layer (stream order / griddepcontrol.wait) waits for
     if (elect_one()) bulk_wait_read_0();
     tc_fence_before();
+}
+
+// dispatch on the layer flags once per kernel (they are uniform): see conv_epilogue_body
+template <int kEpiWarps, bool kF16, bool kAhead, class Origin, class Release>
+static __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint32_t tmem_base, uint64_t* acc_full,
+                                                     uint8_t* epi_stage, uint64_t* res_bar, int ew, int lane,
+                                                     int tile_first, int tile_step, Origin origin, Release release) {
+#define RTOD_EPI(mode) conv_epilogue_body<kEpiWarps, kF16, kAhead, mode>(p, tmem_base, acc_full, epi_stage, res_bar, ew, lane, \
+                                                                         tile_first, tile_step, origin, release)
+    if (p.dbg & (16 | 32)) RTOD_EPI(-1);
+    else if (p.out_fp32) {
+        if (!p.leaky && !p.has_res && !p.w_cat) RTOD_EPI(8);
+        else RTOD_EPI(-1);
+    } else if (p.leaky) {
+        if (p.w_cat) {
+            if (p.has_res) RTOD_EPI(1 | 2 | 4);
+            else RTOD_EPI(1 | 4);
+        } else {
+            if (p.has_res) RTOD_EPI(1 | 2);
+            else RTOD_EPI(1);
+        }
+    } else RTOD_EPI(-1);
+#undef RTOD_EPI
 }
 
 // ------------------------------------------------------------------------------------------------------
