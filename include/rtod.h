@@ -103,7 +103,8 @@ int rtod_plan_bind(RtodPlan* plan, void* workspace, size_t workspace_bytes, void
 
 /* ---- Darknet.load_weights / load_state_dict (src/darknet.py:316-410) -------------------
  * Folds BatchNorm (eval: w' = w*g/sqrt(var+eps), b' = beta - mean*g/sqrt(var+eps)) and
- * re-lays the fp32 [Cout,Cin,k,k] weight out as K-major bf16 [Cout_pad][k*k*Cin] on device.
+ * re-lays the fp32 [Cout,Cin,k,k] weight out as K-major fp16 / bf16 [Cout_pad][k*k*Cin] on device (two-term
+ * layers: hi rows then lo rows).
  * bias may be null (BN convs); the four BN pointers are null for convs without BN. */
 int rtod_plan_set_conv_weights(RtodPlan* plan, int layer, const float* weight, const float* bias,
                                const float* bn_gamma, const float* bn_beta, const float* bn_mean,
