@@ -204,7 +204,7 @@ static __device__ __forceinline__ void conv_epilogue_body(const ConvTcParams& p,
         }
     }
 #ifdef RTOD_TC_TRACE
-    if ((f_dbg & 64) && blockIdx.x == 0 && ew == 0 && lane == 0)
+    if ((p.dbg & 64) && blockIdx.x == 0 && ew == 0 && lane == 0)
         printf("  epilogue warp 0: total %lld clk for %d tiles (%u chunks): acc_full wait %lld, slice wait %lld, tmem ld %lld, "
                "math+res+st.shared %lld, fence+store+res issue %lld\n", clock64() - t_begin, local, g, t_acc, t_slice, t_tmem, t_math, t_store);
 #endif
