@@ -34,6 +34,9 @@
 #include "tc_ptx.cuh"
 
 #include <algorithm>
+#include <array>
+#include <map>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 
@@ -786,6 +789,26 @@ int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cud
     }
     int rc = conv_tc_prepare(a, err_flag, launch, nullptr);              // heuristic choice = fallback
     if (rc || getenv("RTOD_TC_NO_AUTOTUNE")) return rc;
+    // One timing run per layer SHAPE and process: plans of another batch size / resolution, or a re-bound plan, reuse the
+    // choice (re-binding costs milliseconds instead of a second, and every plan of a shape runs the same configuration)
+    using ShapeKey = std::array<long long, 16>;
+    static std::mutex cache_mutex;
+    static std::map<ShapeKey, ConvTcChoice> cache;
+    int device = 0;
+    cudaGetDevice(&device);
+    const ShapeKey key = {a.B, a.in.H, a.in.W, a.Cin, a.Cout, a.Cout_pad, a.ks, a.stride, a.res ? 1 : 0, a.out.fp32, a.in.f16, a.w_split,
+                          a.in.pitch, a.out.pitch, a.res ? a.res_pitch : 0, device};
+    if (getenv("RTOD_TC_NO_TUNE_CACHE") == nullptr) {
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            ConvTcLaunch cached{};
+            if (conv_tc_prepare(a, err_flag, &cached, &it->second) == RTOD_OK) {
+                *launch = cached;
+                return RTOD_OK;
+            }
+        }
+    }
     cudaEvent_t e0, e1;
     RTOD_CUDA_OK(cudaEventCreate(&e0));
     RTOD_CUDA_OK(cudaEventCreate(&e1));
@@ -838,6 +861,12 @@ int conv_tc_autotune(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cud
     cudaEventDestroy(e1);
     if (rc) return rc;
     *launch = best;
+    {
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        ConvTcChoice c = best.choice;
+        c.split = 0;                                       // (by shape, see conv_split_factor)
+        cache[key] = c;
+    }
     if (getenv("RTOD_TC_TUNE_DBG"))
         fprintf(stderr, "conv_tc_autotune: M %d Cin %d Cout %d ks %d s %d -> %s BN %d ctas %d resident %d sbufs %d split %d epi %d aprod %d stages %d pipelines %d row %d (%.1f us)\n",
                 a.B * a.out.H * a.out.W, a.Cin, a.Cout, a.ks, a.stride, best.patch == 2 ? "pair" : "tc", best.choice.bn, best.choice.ctas,
