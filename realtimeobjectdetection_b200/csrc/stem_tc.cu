@@ -1,22 +1,25 @@
 // stem_tc.cu -- the first convolution block (src/darknet.py:488-501 with Cin = 3: 3x3, stride 1, pad 1, BatchNorm
 // folded, leaky 0.1) on the tcgen05 tensor cores, fp16 storage mode.
 //
-// K = 27 is one thin K block, so there is nothing for TMA to gather: the im2col operand is BUILT in shared memory.
-// Per 128-pixel strip of one image row
-//   * a 3-D TMA tiled load stages the 3 rows x 3 channels x (128 + 8) columns neighbourhood (fp32 NCHW planes, or
+// K = 27 is one thin K block, so there is nothing for TMA to gather: the operand is BUILT in shared memory -- and only
+// a third of the im2col matrix is: per 128-pixel strip of one image row
+//   * a 3-D TMA tiled load stages the 3 rows x 3 channels x (128 + halo) columns neighbourhood (fp32 NCHW planes, or
 //     uint8 planes of the pre-processing kernel; halo and image border zero-filled by the TMA bounds check) three
 //     strips ahead;
-//   * 128 "builder" threads, one output pixel each, read their 27 taps from the staged planes (consecutive lanes ->
-//     consecutive words: conflict-free), split every value into two fp16 terms hi + lo and write row t of the
-//     K-major, 64-byte-swizzled operand tiles A_hi / A_lo (32 K values: 27 taps + 5 zeros);
-//   * one thread issues tcgen05.mma: D[128 x 2C] = A_hi * [W_hi | W_lo]^T, then D[:, :C] += A_lo * W_hi^T -- the three
-//     significant products of (a_hi + a_lo)(w_hi + w_lo), ~22 bits of both operands (uint8 frames are exact in one
-//     fp16 term: one MMA group; they enter as value / 256, the weights carry the other 256 / 255 of prep_image's / 255);
-//   * 128 "epilogue" threads read the accumulator (TMEM), add the two column halves and the bias, apply the leaky
-//     slope, round to fp16 and store their pixel's C channels: a warp writes 32 pixels x 2C bytes of contiguous NHWC.
+//   * 128 "builder" threads write ONE operand row per input COLUMN x0-1 .. x0+128 (130 rows): its nine (channel, ky)
+//     values plus a constant 1 (K = 16, the first half of a 64-byte-swizzled row), each value split into two fp16 terms
+//     hi + lo.  The three kx taps are that slab shifted by 0 / 1 / 2 rows: a UMMA descriptor may start at any row of a
+//     swizzled tile (tools/umma_shift64_probe.cu);
+//   * one thread issues, per tap kx, D[128 x 2C] += A_hi(kx) * [W_hi | W_lo](kx)^T and D[:, :C] += A_lo(kx) * W_hi(kx)^T --
+//     the three significant products of (a_hi + a_lo)(w_hi + w_lo), ~22 bits of both operands (uint8 frames are exact
+//     in one fp16 term: one MMA per tap; they enter as value / 256, the weights carry the other 256 / 255 of
+//     prep_image's / 255).  The bias rides on the constant-1 column of the centre tap;
+//   * 128 "epilogue" threads read the accumulator (TMEM), add the two column halves, apply the leaky slope, round to
+//     fp16 and store their pixel's C channels: a warp writes 32 pixels x 2C bytes of contiguous NHWC through TMA.
 // Operand tiles and accumulators are double-buffered; builders of strip i+1 overlap the MMAs and the epilogue of
-// strip i.  Four CTAs per SM.  The previous version (stem.cu: mma.sync fragments built in registers, still used for
-// bf16 storage) spent 24 warp-level MMAs and ~150 issue slots per 16 pixels and ran at 0.3 of the layer's HBM bound.
+// strip i.  Three CTAs per SM.  (History: stem.cu -- mma.sync fragments built in registers, still used for bf16 storage --
+// ran at 0.3 of the layer's HBM bound; the first tcgen05 version built all 27 taps per pixel: three times the builder
+// work of this one.)
 #include <cstdlib>
 
 #include "layers.cuh"
@@ -29,6 +32,8 @@ namespace {
 constexpr int kStages = 3;            // staged input strips in flight
 constexpr int kStrip = 128;           // output pixels per strip = MMA M
 constexpr int kBoxW = kStrip + 8;     // staged columns: 4 left (16-byte alignment of the TMA start), 1 + 3 right
+constexpr int kSlabRows = kStrip + 2; // operand rows per strip: input columns x0-1 .. x0+128
+constexpr uint32_t kATileBytes = ((uint32_t)kSlabRows * 64u + 511u) & ~511u;   // 8704: keeps every tile on a swizzle-pattern boundary
 
 struct StemTcParams {
     CUtensorMap tmX;                  // {W, H, 3*B} fp32 or uint8, box {kBoxW (uint8: kStrip + 32), 3, 3}
@@ -42,6 +47,8 @@ struct StemTcParams {
 
 // byte offset of 16-byte chunk j of row r in a K-major tile of 64-byte rows, SWIZZLE_64B
 __device__ __forceinline__ uint32_t a_row_offset(int r, int j) { return (uint32_t)r * 64u + (((uint32_t)j ^ ((uint32_t)(r >> 1) & 3u)) << 4); }
+// ... of 32-byte rows, SWIZZLE_32B (the weight tiles: K = 16)
+__device__ __forceinline__ uint32_t b_row_offset(int r, int j) { return (uint32_t)r * 32u + (((uint32_t)j ^ ((uint32_t)(r >> 2) & 1u)) << 4); }
 
 // mbarrier wait that parks the warp in hardware for up to ~20 us per attempt instead of spinning through the issue
 // slots the working warps need (128 threads wait at a time here)
@@ -71,11 +78,11 @@ __global__ void __launch_bounds__(288, 3) stem_tc_kernel(const __grid_constant__
     constexpr uint32_t kLeft = kU8 ? 16u : 4u;
     constexpr uint32_t kStageBytes = 9u * kBox * kElem;                              // 3 channels x 3 rows
     constexpr uint32_t kStagePitch = (kStageBytes + 127u) & ~127u;
-    constexpr uint32_t kATile = kStrip * 64u;                                        // 128 rows x 32 fp16
-    // layout: [2 bufs][A_hi | A_lo] | B (2C rows x 64 B) | staged strips | barriers
+    constexpr uint32_t kATile = kATileBytes;                                         // 130 rows x 64 B, rounded up
+    // layout: [2 bufs][A_hi | A_lo] | B [3 taps][2C rows x 32 B] | output staging | staged strips | barriers
     uint8_t* a_tiles = smem;
     uint8_t* b_tile = smem + 4 * kATile;
-    uint8_t* out_stage = b_tile + (size_t)p.C * 128;               // [4 warps][2][32 pixels x 2C bytes], swizzled like the store map
+    uint8_t* out_stage = b_tile + (size_t)p.C * 192;               // [4 warps][2][32 pixels x 2C bytes], swizzled like the store map
     uint8_t* stage0 = out_stage + 8 * (size_t)p.C * 64;
     uint64_t* in_full = reinterpret_cast<uint64_t*>(stage0 + kStages * kStagePitch);
     uint64_t* in_empty = in_full + kStages;        // [kStages] the builders have read staged strip s
@@ -105,20 +112,23 @@ __global__ void __launch_bounds__(288, 3) stem_tc_kernel(const __grid_constant__
     }
     if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)(4 * C < 32 ? 32 : 4 * C));       // 2 buffers x 2C columns
     (void)s_bias;
-    // weights: rows [0, C) = hi terms, [C, 2C) = lo terms of w * in_scale; 32 K values per row (27 taps + zeros)
-    for (int i = tid; i < 2 * C * 4; i += 288) {
-        const int row = i >> 2, j = i & 3, n = row < C ? row : row - C;
+    // weights, one tile per tap kx: rows [0, C) = hi terms, [C, 2C) = lo terms of w * in_scale; 16 K values per row:
+    // k = c*3 + ky (9 taps), k = 9 = the bias (centre tap only: it meets the operand's constant-1 column), zeros
+    for (int i = tid; i < 3 * 2 * C * 2; i += 288) {
+        const int j = i & 1, row = (i >> 1) % (2 * C), kx = i / (4 * C), n = row < C ? row : row - C;
         uint32_t packed[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int k0 = j * 8 + q * 2;
-            // K slot 27 carries the bias: column 27 of the activation operand is the constant 1
-            const float w0 = k0 < 27 ? __ldg(p.w + n * 27 + k0) * p.in_scale : 0.0f;
-            const float w1 = k0 + 1 < 27 ? __ldg(p.w + n * 27 + k0 + 1) * p.in_scale : (k0 + 1 == 27 ? __ldg(p.bias + n) : 0.0f);
-            const uint32_t hi = pack_f16x2(w0, w1);
-            packed[q] = row < C ? hi : pack_f16x2(w0 - f16_lo(hi), w1 - f16_hi(hi));
+            float wv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = j * 8 + q * 2 + e;
+                wv[e] = k < 9 ? __ldg(p.w + n * 27 + k * 3 + kx) * p.in_scale : ((k == 9 && kx == 1) ? __ldg(p.bias + n) : 0.0f);
+            }
+            const uint32_t hi = pack_f16x2(wv[0], wv[1]);
+            packed[q] = row < C ? hi : pack_f16x2(wv[0] - f16_lo(hi), wv[1] - f16_hi(hi));
         }
-        *reinterpret_cast<uint4*>(b_tile + a_row_offset(row, j)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        *reinterpret_cast<uint4*>(b_tile + (size_t)kx * 2 * C * 32 + b_row_offset(row, j)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
     fence_async_smem();
     tc_fence_before();
@@ -161,8 +171,8 @@ __global__ void __launch_bounds__(288, 3) stem_tc_kernel(const __grid_constant__
             };
             for (int l = 0; l < kStages - 1; ++l) issue_load();
             const uint32_t idesc_cat = umma_idesc(1, kStrip, 2 * C), idesc_hi = umma_idesc(1, kStrip, C);
-            const uint64_t desc_tmpl = smem_desc(0u, 64u);
-            const uint64_t db = desc_tmpl | (uint64_t)((smem_u32(b_tile) & 0x3FFFFu) >> 4);
+            const uint64_t desc_tmpl = smem_desc(0u, 64u), descb_tmpl = smem_desc(0u, 32u);
+            const uint32_t b_addr = smem_u32(b_tile);
             for (int local = 0; local < n_mine; ++local) {
                 const int buf = local & 1;
                 const uint32_t use = (uint32_t)(local >> 1);
@@ -172,57 +182,57 @@ __global__ void __launch_bounds__(288, 3) stem_tc_kernel(const __grid_constant__
                 tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)(buf * 2 * C);
                 const uint32_t a_hi = smem_u32(a_tiles + (size_t)buf * 2 * kATile);
-                const uint64_t da = desc_tmpl | (uint64_t)((a_hi & 0x3FFFFu) >> 4);
-                const uint64_t dl = desc_tmpl | (uint64_t)(((a_hi + kATile) & 0x3FFFFu) >> 4);
-                umma_bf16(acc, da, db, idesc_cat, 0u);                              // K steps 0, 1 (+32 bytes)
-                umma_bf16(acc, da + 2, db + 2, idesc_cat, 1u);
-                if (!kU8) {
-                    umma_bf16(acc, dl, db, idesc_hi, 1u);
-                    umma_bf16(acc, dl + 2, db + 2, idesc_hi, 1u);
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {                           // tap kx = the slab shifted by kx rows
+                    const uint64_t da = desc_tmpl | (uint64_t)(((a_hi + (uint32_t)kx * 64u) & 0x3FFFFu) >> 4);
+                    const uint64_t dl = desc_tmpl | (uint64_t)(((a_hi + kATile + (uint32_t)kx * 64u) & 0x3FFFFu) >> 4);
+                    const uint64_t db = descb_tmpl | (uint64_t)(((b_addr + (uint32_t)(kx * 2 * C * 32)) & 0x3FFFFu) >> 4);
+                    umma_bf16(acc, da, db, idesc_cat, kx ? 1u : 0u);
+                    if (!kU8) umma_bf16(acc, dl, db, idesc_hi, 1u);
                 }
                 umma_commit(&a_free[buf]);
                 umma_commit(&acc_full[buf]);
             }
         }
     } else if (warp < 4) {
-        // ================= builders: one output pixel per thread =================
-        uint32_t a_off[4];                                 // this thread's row of the operand tiles
-#pragma unroll
-        for (int j = 0; j < 4; ++j) a_off[j] = a_row_offset(tid, j);
+        // ================= builders: one operand row (= one input column) per thread; threads 0, 1 also rows 128, 129 ====
         for (int local = 0; local < n_mine; ++local) {
             const int s = local % kStages, buf = local & 1;
             const uint32_t use = (uint32_t)(local >> 1);           // how often this buffer has been used before
             // the staged strip has landed; the MMAs that read this operand buffer two strips ago have completed
             mbar_wait_parked(&in_full[s], (uint32_t)(local / kStages) & 1u);
             if (local >= 2) mbar_wait_parked(&a_free[buf], (use - 1u) & 1u);
-            // ---- build row tid of A_hi / A_lo: k = (c*3 + ky)*3 + kx ----
             const uint8_t* st = stage0 + s * kStagePitch;
             uint8_t* a_hi = a_tiles + (size_t)buf * 2 * kATile;
             uint8_t* a_lo = a_hi + kATile;
-            float v[28];
 #pragma unroll
-            for (int r = 0; r < 9; ++r) {                          // r = c*3 + ky: one staged row
-                const uint32_t base = (uint32_t)r * kBox + (uint32_t)tid + kLeft - 1u;
+            for (int pass = 0; pass < 2; ++pass) {
+                const int t = pass == 0 ? tid : kStrip + tid;      // slab row = input column x0 - 1 + t
+                if (pass == 1 && tid >= kSlabRows - kStrip) break;
+                // k = c*3 + ky: the nine staged rows at this column, then the constant 1 that meets the bias, then zeros
+                float v[9];
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx)
-                    v[r * 3 + kx] = kU8 ? (float)st[base + kx] * (1.0f / 256.0f) : reinterpret_cast<const float*>(st)[base + kx];
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&in_empty[s]);              // this warp's taps are in registers
-            v[27] = 1.0f;                                          // x the bias row of the weights
+                for (int r = 0; r < 9; ++r) {
+                    const uint32_t idx = (uint32_t)r * kBox + (uint32_t)t + kLeft - 1u;
+                    v[r] = kU8 ? (float)st[idx] * (1.0f / 256.0f) : reinterpret_cast<const float*>(st)[idx];
+                }
+                uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int k0 = j * 8 + q * 2;
-                    const float x0 = k0 < 28 ? v[k0 < 28 ? k0 : 27] : 0.0f, x1 = k0 + 1 < 28 ? v[k0 + 1 < 28 ? k0 + 1 : 27] : 0.0f;
+                for (int q = 0; q < 8; ++q) {
+                    const float x0 = 2 * q < 9 ? v[2 * q < 9 ? 2 * q : 0] : 0.0f;
+                    const float x1 = 2 * q + 1 < 9 ? v[2 * q + 1 < 9 ? 2 * q + 1 : 0] : (2 * q + 1 == 9 ? 1.0f : 0.0f);
                     hi[q] = pack_f16x2(x0, x1);
                     if (!kU8) lo[q] = pack_f16x2(x0 - f16_lo(hi[q]), x1 - f16_hi(hi[q]));
                 }
-                *reinterpret_cast<uint4*>(a_hi + a_off[j]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                if (!kU8) *reinterpret_cast<uint4*>(a_lo + a_off[j]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<uint4*>(a_hi + a_row_offset(t, 0)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(a_hi + a_row_offset(t, 1)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                if (!kU8) {
+                    *reinterpret_cast<uint4*>(a_lo + a_row_offset(t, 0)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(a_lo + a_row_offset(t, 1)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&in_empty[s]);              // this warp has read its part of the staged strip
             fence_async_smem();                                    // generic-proxy writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_ready[buf]);
@@ -243,26 +253,24 @@ __global__ void __launch_bounds__(288, 3) stem_tc_kernel(const __grid_constant__
             uint8_t* slice = my_stage + (size_t)buf * 32 * row_bytes;
             if (lane == 0) bulk_wait_read_1();                      // the store that last read this slice has drained
             __syncwarp();
-            for (int c0 = 0; c0 < C; c0 += 32) {                   // C = 16: one pass over 16 real columns
-                uint32_t vv[32];
-                tmem_ld_32x32(acc + (uint32_t)c0, vv);             // (C = 16: columns 16.. are the lo half, added below)
-                if (C >= 32) tmem_ld_add_32x32(acc + (uint32_t)(C + c0), vv);
-                else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) vv[j] = __float_as_uint(__uint_as_float(vv[j]) + __uint_as_float(vv[16 + j]));
-                }
-                if (c0 + 32 >= C) {                                // last TMEM read of this strip: hand the buffer back
+            // 16 channels at a time: the hi and the lo accumulator columns are read with ONE wait (this warp's chain of
+            // TMEM round trips is what bounds the kernel), added, activated, rounded and staged
+            for (int c0 = 0; c0 < C; c0 += 16) {
+                uint32_t vh[16], vl[16];
+                tmem_ld_32x16_issue(acc + (uint32_t)c0, vh);
+                tmem_ld_32x16_issue(acc + (uint32_t)(C + c0), vl);
+                tmem_ld_wait();
+                if (c0 + 16 >= C) {                                // last TMEM read of this strip: hand the buffer back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (C == 16 && q >= 2) break;
+                for (int q = 0; q < 2; ++q) {
                     float f[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        f[j] = __uint_as_float(vv[q * 8 + j]);
+                        f[j] = __uint_as_float(vh[q * 8 + j]) + __uint_as_float(vl[q * 8 + j]);
                         if (p.leaky) f[j] = fmaxf(f[j], 0.1f * f[j]);
                     }
                     // 16-byte chunk (c0 / 8 + q) of row `lane`, swizzled like the store's tensor map
@@ -331,7 +339,7 @@ int launch_stem_tc(const float* x_f32, const unsigned char* x_u8, int B, int H, 
         if (ro != CUDA_SUCCESS) return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (stem_tc output) failed: %d", (int)ro);
     }
     const size_t stage_pitch = ((size_t)9 * (u8 ? kStrip + 32 : kBoxW) * (u8 ? 1 : 4) + 127) & ~(size_t)127;
-    const size_t smem = 1024 + 4 * (size_t)kStrip * 64 + (size_t)Cout * 128 + 8 * (size_t)Cout * 64 + kStages * stage_pitch + 512;
+    const size_t smem = 1024 + 4 * (size_t)kATileBytes + (size_t)Cout * 192 + 8 * (size_t)Cout * 64 + kStages * stage_pitch + 512;
     // persistent CTAs: exactly as many as are resident at once (a second wave would double the time).  Residency is
     // computed here from shared memory (64 registers x 256 threads and 4C TMEM columns allow four):
     // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for every kernel that allocates tensor memory.
