@@ -416,13 +416,29 @@ def run_b200(args):
                 tc_ms += ms_arr[i]
                 tc_flops += lib.rtod_plan_layer_flops(plan.handle, i)
     cfg12 = (ctypes.c_int * 12)()
+    from realtimeobjectdetection_b200 import synth as _synth
+    table = _synth.layer_table(blocks)
+    c_, h_, w_ = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     for i in range(n_layers):
         if kind_arr[i]:
             row = [i, int(kind_arr[i]), round(float(ms_arr[i]), 4),
                    round(lib.rtod_plan_layer_flops(plan.handle, i) / max(ms_arr[i], 1e-6) / 1e9, 1)]
             if kind_arr[i] == 1 and lib.rtod_plan_conv_config(plan.handle, i, cfg12) == 0:
-                row.append({"pair": int(cfg12[0] == 3), "bn": cfg12[1], "ctas": cfg12[2], "resident": cfg12[3],
-                            "pipelines": cfg12[8], "stages": cfg12[9], "two_term_weights": cfg12[10]})
+                info = {"pair": int(cfg12[0] == 3), "bn": cfg12[1], "ctas": cfg12[2], "resident": cfg12[3],
+                        "pipelines": cfg12[8], "stages": cfg12[9], "two_term_weights": cfg12[10]}
+                # the layer's own roofline: max(FLOP / sustained tensor peak, algorithmic bytes / HBM peak) against its
+                # measured time (which carries the 2-5 us of its profiling events)
+                t = table[i]
+                lib.rtod_plan_layer_shape(plan.handle, i, ctypes.byref(c_), ctypes.byref(h_), ctypes.byref(w_))
+                out_px = B * h_.value * w_.value
+                in_px = out_px * t["stride"] * t["stride"]
+                head = i + 1 < len(table) and table[i + 1]["type"] == "yolo"
+                res = i + 1 < len(table) and table[i + 1]["type"] == "shortcut"
+                nbytes = in_px * t["cin"] * 2 + out_px * t["cout"] * (4 if head else 2) * (2 if res else 1) + t["cout"] * t["cin"] * t["size"] ** 2 * 2
+                bound_ms = max(lib.rtod_plan_layer_flops(plan.handle, i) / (peaks["tflops_sustained"] * 1e9), nbytes / (peaks["hbm_gbs"] * 1e6))
+                info["bound_us"] = round(bound_ms * 1e3, 1)
+                info["frac_of_bound"] = round(bound_ms / max(float(ms_arr[i]), 1e-9), 3)
+                row.append(info)
             per_layer.append(row)
     n_tc = sum(1 for i in range(n_layers) if kind_arr[i] == 1)
     # the figure that is reported: CUDA events only where the stream switches between the tcgen05 convolution
