@@ -846,7 +846,7 @@ extern "C" int rtod_write_results(const float* pred, int B, int N, int C, float 
 
     // ---- scan -----------------------------------------------------------------------------
     const long long total_rows = (long long)B * N;
-    static const bool stream_scan = getenv("RTOD_NMS_STREAM") != nullptr;     // the tensor-streaming scan (comparison runs)
+    const bool stream_scan = getenv("RTOD_NMS_STREAM") != nullptr;            // the tensor-streaming scan (comparison runs, tests)
     if (!stream_scan) {
         const long long n_blocks = (total_rows + 32 * kSparseGroups - 1) / (32 * kSparseGroups);
         long long grid = (n_blocks + kSparseThreads / 32 - 1) / (kSparseThreads / 32);
@@ -891,12 +891,12 @@ extern "C" int rtod_write_results(const float* pred, int B, int N, int C, float 
     cfg.stream = stream;
     cfg.attrs = pdl;
     cfg.numAttrs = 1;
-    static const bool no_fused = getenv("RTOD_NMS_NO_FUSED_EMIT") != nullptr;
+    const bool no_fused = getenv("RTOD_NMS_NO_FUSED_EMIT") != nullptr;        // light / heavy pass + emit kernel for every batch size
     if (B <= kNumSMs && !no_fused) {
         // resident launch: one CTA per image and SM, every image size in one configuration, emit fused (the CTAs wait
         // for their predecessors' counts, which needs all of them on the machine at once)
         const int hcap = lay.P < kSortSmemCap ? lay.P : kSortSmemCap;
-        static const int threads = getenv("RTOD_NMS_THREADS") ? atoi(getenv("RTOD_NMS_THREADS")) : kImageThreads;
+        const int threads = getenv("RTOD_NMS_THREADS") ? atoi(getenv("RTOD_NMS_THREADS")) : kImageThreads;
         cfg.blockDim = dim3((unsigned)(threads >= 128 && threads <= kImageThreads && threads % 32 == 0 ? threads : kImageThreads), 1, 1);
         cfg.dynamicSmemBytes = (size_t)hcap * 12 + hcap / 8 + kBoxCap * 20;
         RTOD_CUDA_OK(cudaLaunchKernelEx(&cfg, nms_image_kernel, pred, N, L, confidence, nms_conf, lay.P,

@@ -108,6 +108,23 @@ def test_write_results_ragged_shapes(B, N, C, conf, nms):
     assert rows_equal(got, want)
 
 
+@pytest.mark.parametrize("density,clustered", [(0.01, False), (0.10, True), (0.50, True)])
+def test_write_results_every_kernel_path_agrees(monkeypatch, density, clustered):
+    """sparse scan + resident pass with fused emit (default, B <= 148)  ==  tensor-streaming scan + light / heavy pass +
+    emit kernel (what B > 148 runs, forced here)  ==  the oracle"""
+    pred = torch.from_numpy(synth_pred(21, 3, 10647, 80, density, clustered))
+    want = oracle.write_results(pred.clone(), 80, 0.5, 0.4)
+    outs = [write_results(pred.cuda(), 80, 0.5, 0.4)]
+    monkeypatch.setenv("RTOD_NMS_NO_FUSED_EMIT", "1")
+    outs.append(write_results(pred.cuda(), 80, 0.5, 0.4))
+    monkeypatch.setenv("RTOD_NMS_STREAM", "1")
+    outs.append(write_results(pred.cuda(), 80, 0.5, 0.4))
+    monkeypatch.delenv("RTOD_NMS_NO_FUSED_EMIT")
+    outs.append(write_results(pred.cuda(), 80, 0.5, 0.4))
+    for o in outs:
+        assert rows_equal(o, want)
+
+
 def test_write_results_dense_single_class_global_sort_path():
     """> 16384 candidates in one image: the kernel sorts in global memory instead of shared."""
     pred = torch.from_numpy(synth_pred(3, 1, 22743, 2, 0.9, True, span=608.0))
