@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
                         if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);   // both CTAs' bytes
                         if (p.ks > 1) tma_load_im2col_4d_pair(a_dst, &p.tmA, lead_full, c0, ow, oh, on, off_w, off_h);
                         else tma_load_2d_pair(a_dst, &p.tmA, lead_full, c0, m0);
-                        tma_load_2d_pair(a_dst + a_bytes, &p.tmB, lead_full, k0, nrow0);
-                        if (p.w_split) tma_load_2d_pair(a_dst + a_bytes + b_half, &p.tmB, lead_full, k0, p.cout_pad + nrow0);
+                        // (K-block-major packed weights, BK == PK: block k0 / BK, column 0)
+                        tma_load_3d_pair(a_dst + a_bytes, &p.tmB, lead_full, 0, nrow0, k0 >> p.pack_shift);
+                        if (p.w_split) tma_load_3d_pair(a_dst + a_bytes + b_half, &p.tmB, lead_full, 0, p.cout_pad + nrow0, k0 >> p.pack_shift);
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1u;
@@ -323,10 +324,13 @@ int conv_pair_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch) {
     }
     if (r != CUDA_SUCCESS) return fail(RTOD_ERR_CUDA, "cuTensorMapEncode (pair activations) failed: %d", (int)r);
     {
-        const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)(a.Cout_pad << a.w_split)};
-        const cuuint64_t strides[1] = {(cuuint64_t)a.K * 2};
-        const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(BN / 2)};
-        r = encode_tiled(&p.tmB, h16_tmap_type(a.in.f16), 2, const_cast<void*>(a.w), dims, strides,
+        p.pack_k = BK;                                     // (= weight_pack_k(Cin, K): the pair kernel's K tile is pick_bk(Cin))
+        p.pack_shift = BK == 64 ? 6 : (BK == 32 ? 5 : 4);
+        const cuuint64_t rows = (cuuint64_t)(a.Cout_pad << a.w_split);
+        const cuuint64_t dims[3] = {(cuuint64_t)BK, rows, (cuuint64_t)(a.K / BK)};
+        const cuuint64_t strides[2] = {(cuuint64_t)BK * 2, rows * BK * 2};
+        const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(BN / 2), 1};
+        r = encode_tiled(&p.tmB, h16_tmap_type(a.in.f16), 3, const_cast<void*>(a.w), dims, strides,
                          box, estr1, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (pair weights) failed: %d", (int)r);

@@ -53,8 +53,9 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
             const int k = k0 + kk, n = n0 + nn;
             float wv = 0.0f;
             if (k < a.K && n < a.Cout) {
-                wv = h1_to_float<kF16>(w16[(long long)n * a.K + k]);
-                if (a.w_split) wv += h1_to_float<kF16>(w16[(long long)(a.Cout_pad + n) * a.K + k]);      // hi + lo
+                const int rows = a.Cout_pad << a.w_split, PK = weight_pack_k(a.Cin, a.K);
+                wv = h1_to_float<kF16>(w16[packed_weight_index(n, k, rows, PK)]);
+                if (a.w_split) wv += h1_to_float<kF16>(w16[packed_weight_index(a.Cout_pad + n, k, rows, PK)]);      // hi + lo
             }
             Bs[kk][nn] = wv;
         }

@@ -281,8 +281,10 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
               if (sub == 0) {
                 mbar_expect_tx(wres_bar, (uint32_t)num_kb * b_bytes);
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    tma_load_2d(b_resident + (size_t)kb * b_bytes, &p.tmB, wres_bar, kb * p.BK, 0);
-                    if (p.w_split) tma_load_2d(b_resident + (size_t)kb * b_bytes + b_half, &p.tmB, wres_bar, kb * p.BK, p.cout_pad);
+                    // weights are K-block-major {PK, rows, K / PK} (layers.cuh): (column inside the block, row, block)
+                    const int kc = (kb * p.BK) & (p.pack_k - 1), kblk = (kb * p.BK) >> p.pack_shift;
+                    tma_load_3d(b_resident + (size_t)kb * b_bytes, &p.tmB, wres_bar, kc, 0, kblk);
+                    if (p.w_split) tma_load_3d(b_resident + (size_t)kb * b_bytes + b_half, &p.tmB, wres_bar, kc, p.cout_pad, kblk);
                 }
               }
             } else {
@@ -296,9 +298,10 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
                     for (int k0 = kb0 * p.BK; k0 < kb1 * p.BK; k0 += p.BK) {
                         if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag)) { ok = false; break; }
                         mbar_expect_tx(&full_bar[stage], b_bytes);
-                        tma_load_2d(ring + (size_t)stage * stage_bytes + a_bytes, &p.tmB, &full_bar[stage], k0, n0);
+                        const int kc = k0 & (p.pack_k - 1), kblk = k0 >> p.pack_shift;
+                        tma_load_3d(ring + (size_t)stage * stage_bytes + a_bytes, &p.tmB, &full_bar[stage], kc, n0, kblk);
                         if (p.w_split)
-                            tma_load_2d(ring + (size_t)stage * stage_bytes + a_bytes + b_half, &p.tmB, &full_bar[stage], k0, p.cout_pad + n0);
+                            tma_load_3d(ring + (size_t)stage * stage_bytes + a_bytes + b_half, &p.tmB, &full_bar[stage], kc, p.cout_pad + n0, kblk);
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1u;
@@ -730,13 +733,18 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
     if (r != CUDA_SUCCESS)
         return fail(RTOD_ERR_CUDA, "cuTensorMapEncode (activations, ks=%d Cin=%d pitch=%d) failed: %d", a.ks,
                     a.Cin, a.in.pitch, (int)r);
-    // ---- B ----
+    // ---- B: K-block-major packed weights {PK, rows, K / PK} (layers.cuh): every box is one contiguous block ----
     {
-        const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)(a.Cout_pad << a.w_split)};
-        const cuuint64_t strides[1] = {(cuuint64_t)a.K * 2};
-        const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
-        r = encode_tiled(&p.tmB, h16_tmap_type(a.in.f16), 2, const_cast<void*>(a.w), dims,
-                         strides, box, estr1, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK),
+        const int PK = weight_pack_k(a.Cin, a.K);
+        p.pack_k = PK;
+        p.pack_shift = PK == 64 ? 6 : (PK == 32 ? 5 : 4);
+        const cuuint64_t rows = (cuuint64_t)(a.Cout_pad << a.w_split);
+        const cuuint64_t dims[3] = {(cuuint64_t)PK, rows, (cuuint64_t)(a.K / PK)};
+        const cuuint64_t strides[2] = {(cuuint64_t)PK * 2, rows * PK * 2};
+        const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
+        const cuuint32_t estr3[3] = {1, 1, 1};
+        r = encode_tiled(&p.tmB, h16_tmap_type(a.in.f16), 3, const_cast<void*>(a.w), dims,
+                         strides, box, estr3, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK),
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS)
             return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (weights, K=%d Cout_pad=%d) failed: %d", a.K,

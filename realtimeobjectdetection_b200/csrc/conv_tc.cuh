@@ -9,7 +9,7 @@ namespace rtod {
 // Everything one launch needs; built once at plan-bind time (the tensor maps embed addresses).
 struct alignas(64) ConvTcParams {
     CUtensorMap tmA;            // activations: 2-D tiled {C, M} (1x1) or 4-D im2col {C, W, H, N} (3x3)
-    CUtensorMap tmB;            // weights: 2-D tiled {K, Cout_pad}
+    CUtensorMap tmB;            // weights: 3-D tiled {PK, rows, K / PK}, K-block-major (layers.cuh)
     CUtensorMap tmOut;          // output: 2-D tiled {Cout, M}, NHWC bf16 (fp32 for head logits)
     CUtensorMap tmRes;          // shortcut operand: 2-D tiled {Cout, M} bf16 (valid iff has_res)
     const float* bias;          // [Cout_pad]
@@ -47,6 +47,7 @@ struct alignas(64) ConvTcParams {
     uint32_t fd_segs[3], fd_ho[3];
     int a_prefetch;             // activation tiles prefetched into L2 this many of the CTA's tiles ahead (0 = off): layers that
                                 // stream their input from HBM are bound by latency x bytes in flight, and the ring is small
+    int pack_k, pack_shift;     // K block of the packed weight layout (16 / 32 / 64) and its log2
     int lo_col;                 // column distance from a value's hi term to its lo term (w_cat): BN, pair kernel BN / 2
     int split_k, split_shift;   // K slices per output tile (power of two, 1 = off) and log2 of it
     float* split_scratch;       // [total_tiles][split_k][128][BN] fp32 partial accumulators

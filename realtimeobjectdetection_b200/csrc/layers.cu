@@ -386,9 +386,10 @@ __global__ void fold_pack_kernel(const float* __restrict__ w, const float* __res
         const float scale = gamma ? gamma[o] * (1.0f / sqrtf(var[o] + eps)) : 1.0f;
         const float v = w[i] * scale;
         const unsigned short hi = float_to_h1<kF16>(v);
-        wp[(long long)o * K + (long long)t * Cin + c] = hi;
+        const int rows = Cout_pad << w_split, PK = weight_pack_k(Cin, K), k = t * Cin + c;
+        wp[packed_weight_index(o, k, rows, PK)] = hi;
         if (w_split)                                         // second term of the two-term weight (rows Cout_pad ..)
-            wp[(long long)(Cout_pad + o) * K + (long long)t * Cin + c] = float_to_h1<kF16>(v - h1_to_float<kF16>(hi));
+            wp[packed_weight_index(Cout_pad + o, k, rows, PK)] = float_to_h1<kF16>(v - h1_to_float<kF16>(hi));
         if (wf) wf[i] = v;
         if (r == 0) {
             float bv = bias ? bias[o] : 0.0f;

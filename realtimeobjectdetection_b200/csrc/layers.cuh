@@ -15,9 +15,19 @@ struct Act {
     int f16;                    // 16-bit elements are fp16 (1) or bf16 (0); ignored when fp32
 };
 
+// Packed weight layout (fold_pack_kernel): K-BLOCK-major, [K / PK][rows][PK] 16-bit elements, rows = Cout_pad (two-term
+// weights: hi rows then lo rows, 2 * Cout_pad), K = (ky*ks + kx)*Cin + c, PK = weight_pack_k(Cin, K) = the K tile of the
+// tcgen05 kernels.  Any run of consecutive rows of one K block -- every weight tile the kernels load -- is ONE contiguous
+// block of memory: a TMA box whose 128-byte rows are adjacent streams at ~74 B/clk/SM from L2, rows that lie a pitch
+// apart (the plain [rows][K] layout) at ~49 (tools/tma_multicast_probe.cu).
+__host__ __device__ inline int weight_pack_k(int cin, int K) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : (cin % 16 == 0 ? 16 : K)); }
+__host__ __device__ inline size_t packed_weight_index(int n, int k, int rows, int PK) {
+    return ((size_t)(k / PK) * (size_t)rows + (size_t)n) * (size_t)PK + (size_t)(k % PK);
+}
+
 struct ConvArgs {
     Act in, out;
-    const void* w;              // [Cout_pad][K] K-major fp16/bf16, K = (ky*ks + kx)*Cin + c, BN folded
+    const void* w;              // packed weights (see packed_weight_index), BN folded
     const float* bias;          // [Cout_pad] fp32 (BN folded)
     const void* res;            // optional shortcut operand, same pixels/channels as out
     int res_pitch;

@@ -289,6 +289,14 @@ static __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtenso
         "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
         : "memory");
 }
+static __device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr,
+                                                        int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 static __device__ __forceinline__ void tma_load_im2col_4d_pair(void* dst, const CUtensorMap* map,
                                                                uint32_t bar_cluster_addr, int c, int w, int h, int n,
                                                                uint16_t off_w, uint16_t off_h) {
