@@ -405,3 +405,32 @@ def test_streaming_pipeline_uint8_frames():
     for b, det in zip(batches, got):
         want = write_results(model(prep_frames(b, 320, as_uint8=True)), 80, 0.5, 0.4)
         assert rows_equal(det, want)
+
+
+def test_sharded_detection_over_nccl_single_rank():
+    """The multi-GPU entry points on the NCCL backend (the driver's test tier has one GPU: world size 1; the world-2
+    logic runs on gloo in test_host_cpu.py): detect_sharded, the synchronous gather and the fixed-capacity asynchronous
+    gather return exactly write_results' rows; a pipeline with gather= yields the same."""
+    import torch.distributed as dist
+    from realtimeobjectdetection_b200.pipeline import DetectionPipeline
+    from realtimeobjectdetection_b200.sharding import detect_sharded, gather_detections, gather_detections_async
+    from realtimeobjectdetection_b200.util import write_results_async
+    cfg, blocks, stream, state = make_network("yolov3-tiny", 8, "calibrated")
+    model = build_model(cfg, state, 224)
+    x = torch.from_numpy(np.random.RandomState(4).rand(3, 3, 224, 224).astype(np.float32))
+    want = write_results(model(x.cuda()), 80, 0.3, 0.4)
+    assert not isinstance(want, int)
+    port = 29600 + os.getpid() % 300
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, world_size=1, rank=0,
+                            device_id=torch.device("cuda", torch.cuda.current_device()))
+    try:
+        assert torch.equal(detect_sharded(model, x.cuda(), 80, 0.3, 0.4).cpu(), want.cpu())
+        assert torch.equal(gather_detections(want, 0).cpu(), want.cpu())
+        h = write_results_async(model(x.cuda()), 80, 0.3, 0.4)
+        got = gather_detections_async(h.rows_device, h.count_device, 0, capacity=want.size(0) + 5).result()
+        assert torch.equal(got, want.cpu())
+        pipe = DetectionPipeline(model, 80, 0.3, 0.4, gather={"first_frame": 0, "capacity": want.size(0) + 5})
+        outs = list(pipe.run([x.pin_memory(), x.pin_memory()]))
+        assert len(outs) == 2 and all(torch.equal(o, want.cpu()) for o in outs)
+    finally:
+        dist.destroy_process_group()
