@@ -151,6 +151,10 @@ class PendingDetections:
                 out.copy_(self._rows[:d], non_blocking=True)      # rows are final since `event`
             side.synchronize()
             return out
+        # the row buffer is this call's own allocation: for small batches hand out a view of it (one launch less on the
+        # batch-1 latency path); for large ones copy the few detections out and let the [B*N, 8] buffer go
+        if self._rows.numel() * 4 <= (1 << 20):
+            return self._rows[:d]
         return self._rows[:d].clone()
 
 
