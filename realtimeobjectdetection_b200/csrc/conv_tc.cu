@@ -51,6 +51,7 @@ static uint32_t resident_limit() {
     static const uint32_t v = getenv("RTOD_TC_RESIDENT_KB") ? (uint32_t)atoi(getenv("RTOD_TC_RESIDENT_KB")) * 1024u : 100u * 1024u;
     return v;
 }
+constexpr uint32_t kResidentLimitForced = 160 * 1024;  // ... that a forced (autotuned) configuration may keep resident
 constexpr uint32_t kResidentLimitRow = 150 * 1024;   // row mode (always resident; its stages are small slabs)
 constexpr int kSlabRows = kBM + 2;              // row mode: input pixels x0-1 .. x0+128 of one image row
 
@@ -162,6 +163,17 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
                 ptr += n;
                 left -= n;
             }
+        }
+    }
+    if (p.b_resident && warp == 2 && sub == 0 && elect_one()) {
+        // resident weights: the whole [BN x K] weight matrix (single N tile), once per CTA.  Weights are written at
+        // weight-sync time, never by the previous layer: the load starts before the dependency wait
+        mbar_expect_tx(wres_bar, (uint32_t)num_kb * b_bytes);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            // weights are K-block-major {PK, rows, K / PK} (layers.cuh): (column inside the block, row, block)
+            const int kc = (kb * p.BK) & (p.pack_k - 1), kblk = (kb * p.BK) >> p.pack_shift;
+            tma_load_3d(b_resident + (size_t)kb * b_bytes, &p.tmB, wres_bar, kc, 0, kblk);
+            if (p.w_split) tma_load_3d(b_resident + (size_t)kb * b_bytes + b_half, &p.tmB, wres_bar, kc, p.cout_pad, kblk);
         }
     }
     pdl_wait();                          // everything above overlapped the previous layer's tail
@@ -277,17 +289,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     } else if (warp == 2) {
         // ================= TMA producer B: weight tiles (ring), or the whole matrix once =================
         if (elect_one()) {
-            if (p.b_resident) {                  // single N tile: the whole [BN x K] weight matrix, once per CTA
-              if (sub == 0) {
-                mbar_expect_tx(wres_bar, (uint32_t)num_kb * b_bytes);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    // weights are K-block-major {PK, rows, K / PK} (layers.cuh): (column inside the block, row, block)
-                    const int kc = (kb * p.BK) & (p.pack_k - 1), kblk = (kb * p.BK) >> p.pack_shift;
-                    tma_load_3d(b_resident + (size_t)kb * b_bytes, &p.tmB, wres_bar, kc, 0, kblk);
-                    if (p.w_split) tma_load_3d(b_resident + (size_t)kb * b_bytes + b_half, &p.tmB, wres_bar, kc, p.cout_pad, kblk);
-                }
-              }
-            } else {
+            if (!p.b_resident) {                 // (resident weights: loaded above, ahead of the dependency wait)
                 int stage = 0;
                 uint32_t phase = 0;
                 bool ok = true;
@@ -590,7 +592,10 @@ int conv_tc_prepare(const ConvArgs& a, int* err_flag, ConvTcLaunch* launch, cons
     // resident weights if that is what makes them fit; fat tiles (BN = 256) keep one CTA per SM,
     // eight epilogue warps and the deepest operand ring that fits.
     const uint32_t w_bytes = (uint32_t)(BN << a.w_split) * a.K * 2;
-    const bool may_reside = a.Cout_pad == BN && w_bytes <= (row ? kResidentLimitRow : resident_limit()) &&
+    // (a forced configuration -- the bind-time autotuner's candidates -- may keep a larger matrix resident than the
+    // heuristic would: the 128 KB of a two-term 256 -> 128 1x1 layer next to a four-stage activation ring)
+    const uint32_t res_limit = row ? kResidentLimitRow : (force && force->resident == 1 ? std::max(resident_limit(), kResidentLimitForced) : resident_limit());
+    const bool may_reside = a.Cout_pad == BN && w_bytes <= res_limit &&
                             (row || getenv("RTOD_TC_NO_RESIDENT") == nullptr);
     p.row_mode = row;
     p.slab_bytes = ((uint32_t)kSlabRows * BK * 2 + 1023u) & ~1023u;

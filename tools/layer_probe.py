@@ -25,7 +25,8 @@ LAYERS = {
     "L12": (128, 256, 3, 2, 104, 0), "L13": (256, 128, 1, 1, 52, 0), "L14": (128, 256, 3, 1, 52, 1),
     "L37": (256, 512, 3, 2, 52, 0), "L38": (512, 256, 1, 1, 26, 0), "L39": (256, 512, 3, 1, 26, 1),
     "L62": (512, 1024, 3, 2, 26, 0), "L63": (1024, 512, 1, 1, 13, 0), "L64": (512, 1024, 3, 1, 13, 1),
-    "L99": (384, 128, 1, 1, 52, 0), "L105": (256, 255, 1, 1, 52, 0),
+    "L99": (384, 128, 1, 1, 52, 0), "L105": (256, 255, 1, 1, 52, 0), "L81": (1024, 255, 1, 1, 13, 0),
+    "L87": (768, 256, 1, 1, 26, 0), "L93": (512, 255, 1, 1, 26, 0), "L76": (512, 1024, 3, 1, 13, 0),
 }
 
 
