@@ -1,9 +1,11 @@
 // decode.cu -- util.predict_transform (src/util.py:175-239) on the GPU.
 //
 // Two entry points share one element transform:
-//   * yolo_decode_nchw_kernel: the drop-in for predict_transform(): an NCHW fp32 head
-//     [B, A*(5+C), G, G] is transposed through shared memory (coalesced 128-byte reads along
-//     the cell axis, coalesced writes along the attribute axis) into [B, G*G*A, 5+C];
+//   * yolo_decode_nchw_tma_kernel / yolo_decode_nchw_kernel: the drop-in for predict_transform(): an
+//     NCHW fp32 head [B, A*(5+C), G, G] is transposed through shared memory (128-byte reads along the
+//     cell axis, coalesced writes along the attribute axis) into [B, G*G*A, 5+C]; persistent CTAs fed
+//     by a TMA tile ring when the channel rows are 16-byte aligned (G*G % 4 == 0), one tile per CTA
+//     otherwise;
 //   * yolo_decode_heads_kernel: used inside the forward plan: the head convolutions leave
 //     their fp32 logits in NHWC (pixel-major) buffers, which is already the row order of
 //     the prediction tensor, so ONE launch decodes all yolo heads element-wise and writes
@@ -15,6 +17,7 @@
 #include <cstdlib>
 
 #include "decode.cuh"
+#include "tc_ptx.cuh"
 
 namespace rtod {
 
@@ -32,17 +35,34 @@ __device__ __forceinline__ float decode_value(float v, int attr, int cell_x, int
     return __fmul_rn(__fmul_rn(expf(v), attr == 2 ? aw : ah), stride);
 }
 
-constexpr int kTileCells = 32;
-constexpr int kTileCh = 256;
-
+// tile: kTileCh channels x kTileCells cells (32 KB of shared memory)
+template <int kTileCh, int kTileCells>
 __global__ void __launch_bounds__(256)
-yolo_decode_nchw_kernel(const float* __restrict__ head, int G, int A, int L, float stride, int train, int exact,
+yolo_decode_nchw_kernel(const float* __restrict__ head, int G, int A, int L, float stride, int train, int exact, int vec,
                         DecodeAnchors anchors, float* __restrict__ out) {
-    __shared__ float tile[kTileCh][kTileCells + 1];
+    extern __shared__ float tile_raw[];
+    float (*tile)[kTileCells + 1] = reinterpret_cast<float (*)[kTileCells + 1]>(tile_raw);
     const int GG = G * G, Ch = A * L;
     const int cell0 = blockIdx.x * kTileCells, ch0 = blockIdx.z * kTileCh, b = blockIdx.y;
     const int n_ch = min(kTileCh, Ch - ch0), n_cell = min(kTileCells, GG - cell0);
     const float* src = head + ((long long)b * Ch + ch0) * GG + cell0;
+    if (vec && n_cell == kTileCells) {
+        // whole tile, 16-byte aligned rows (G*G % 4 == 0): every thread has its eight 16-byte loads in flight at once
+        // (32 KB per CTA; the scalar loop below keeps a few hundred bytes per warp in flight and is latency-bound);
+        // a warp covers four channels x 128 B, its shared-memory writes (row pitch 33 words) are conflict-free
+        constexpr int kPerRow = kTileCells / 4, kLoads = kTileCh * kPerRow / 256;
+        float4 v[kLoads];
+#pragma unroll
+        for (int k = 0; k < kLoads; ++k) {
+            const int j = threadIdx.x + 256 * k, ch = j / kPerRow;
+            v[k] = ch < n_ch ? __ldcs(reinterpret_cast<const float4*>(src + (long long)ch * GG) + (j % kPerRow)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < kLoads; ++k) {
+            const int j = threadIdx.x + 256 * k, ch = j / kPerRow, cl = (j % kPerRow) * 4;
+            tile[ch][cl] = v[k].x; tile[ch][cl + 1] = v[k].y; tile[ch][cl + 2] = v[k].z; tile[ch][cl + 3] = v[k].w;
+        }
+    } else
     for (int i = threadIdx.x; i < n_ch * kTileCells; i += 256) {
         const int ch = i / kTileCells, cl = i % kTileCells;
         tile[ch][cl] = cl < n_cell ? src[(long long)ch * GG + cl] : 0.0f;
@@ -53,33 +73,160 @@ yolo_decode_nchw_kernel(const float* __restrict__ head, int G, int A, int L, flo
     // anchor, one lane each, in the reference's op order (same scheme as yolo_decode_heads_fast_kernel)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned plain = 0;
+    {   // attribute of channel ch0 + lane + 32 i: one modulo, then carried additions (an integer modulo by a run-time
+        // value costs ~30 instructions; eight of them per thread were a fifth of this kernel's instruction stream)
+        int attr = (int)((unsigned)(ch0 + lane) % (unsigned)L);
 #pragma unroll
-    for (int i = 0; i < kTileCh / 32; ++i) {
-        const int chl = lane + 32 * i;
-        if (chl < n_ch && (ch0 + chl) % L >= 4) plain |= 1u << i;
+        for (int i = 0; i < kTileCh / 32; ++i) {
+            if (lane + 32 * i < n_ch && attr >= 4) plain |= 1u << i;
+            attr += 32;
+            while (attr >= L) attr -= L;
+        }
     }
-    for (int cl = warp; cl < n_cell; cl += 8) {
-        const int cell = cell0 + cl;
-        const int cy = cell / G, cx = cell - cy * G;
-        float* dst = out + ((long long)b * GG + cell) * Ch + ch0;
+    constexpr int kWarps = 8;
+    for (int cl = warp; cl < n_cell; cl += kWarps) {
+        float* dst = out + ((long long)b * GG + cell0 + cl) * Ch + ch0;
 #pragma unroll
         for (int i = 0; i < kTileCh / 32; ++i) {
             const float r = exact ? sigmoid_f32(tile[lane + 32 * i][cl]) : sigmoid_fast_f32(tile[lane + 32 * i][cl]);
             if ((plain >> i) & 1u) __stcs(dst + lane + 32 * i, r);
         }
-        if (lane < 4 * A) {
-            const int a = lane >> 2, attr = lane & 3, chl = a * L + attr - ch0;
-            if (chl >= 0 && chl < n_ch) {
-                const float v = tile[chl][cl];
-                float r;
-                if (attr < 2) {
-                    r = sigmoid_f32(v);
-                    if (!train) r = __fmul_rn(__fadd_rn(r, (float)(attr == 0 ? cx : cy)), stride);
-                } else {
-                    r = train ? v : __fmul_rn(__fmul_rn(expf(v), attr == 2 ? anchors.w[a] : anchors.h[a]), stride);
+    }
+    // fix-up: the 4 box attributes of each anchor in the reference's op order, one THREAD per (cell, anchor, attribute)
+    // over the whole tile -- the full-precision expf / division chain is ~80 dependent instructions; run per cell by
+    // twelve lanes of a warp it took longer than the main pass
+    const int per_cell = 4 * A;
+    for (int it = threadIdx.x; it < n_cell * per_cell; it += 256) {
+        const int cl = it / per_cell, rem = it - cl * per_cell, a = rem >> 2, attr = rem & 3, chl = a * L + attr - ch0;
+        if (chl < 0 || chl >= n_ch) continue;
+        const int cell = cell0 + cl, cy = cell / G, cx = cell - cy * G;
+        const float v = tile[chl][cl];
+        float r;
+        if (attr < 2) {
+            r = sigmoid_f32(v);
+            if (!train) r = __fmul_rn(__fadd_rn(r, (float)(attr == 0 ? cx : cy)), stride);
+        } else {
+            float anchor = 0.0f;
+#pragma unroll
+            for (int q = 0; q < RTOD_MAX_ANCHORS; ++q)           // (a run-time index into the by-value arrays would go through local memory)
+                if (q == a) anchor = attr == 2 ? anchors.w[q] : anchors.h[q];
+            r = train ? v : __fmul_rn(__fmul_rn(expf(v), anchor), stride);
+        }
+        __stcs(out + ((long long)b * GG + cell) * Ch + ch0 + chl, r);
+    }
+}
+
+// TMA-pipelined variant of yolo_decode_nchw_kernel (G*G % 4 == 0, A*(5+C) <= 256): persistent CTAs, one producer thread
+// keeps `stages` 32 KB tiles (256 channel rows x 32 cells, 128-byte rows, SWIZZLE_128B) in flight with 3-D tiled TMA loads
+// of the NCHW head {cells, channels, images}; eight consumer warps decode tile n while tiles n+1 .. n+stages-1 are landing.
+// The load -> barrier -> store phases of the one-tile-per-CTA kernel never overlap inside a CTA; here the stores of one
+// tile always run under the loads of the next ones.  Channel row 255 and cells beyond G*G are zero-filled by the TMA
+// bounds check.  Reading column `cl` of 32 different rows from the swizzled tile is a 4-way bank conflict (8 distinct
+// 16-byte slots per 128-byte row): 256 such reads per tile, far from the shared-memory limit.
+constexpr int kTmaTileCells = 32, kTmaTileCh = 256, kTmaConsumers = 256;
+constexpr uint32_t kTmaTileBytes = kTmaTileCells * kTmaTileCh * 4;
+
+__device__ __forceinline__ bool decode_wait(uint64_t* bar, uint32_t parity) {     // bounded: never hangs the GPU
+    for (unsigned spins = 0; spins < (1u << 26); ++spins)
+        if (mbar_try_wait(bar, parity)) return true;
+    return false;
+}
+__device__ __forceinline__ float swz_tile(const uint8_t* tile, int ch, int cl) {  // element (ch, cl) of a SWIZZLE_128B tile
+    return *reinterpret_cast<const float*>(tile + ch * 128 + ((((cl >> 2) ^ (ch & 7))) << 4) + ((cl & 3) << 2));
+}
+
+template <bool kExact>
+__global__ void __launch_bounds__(kTmaConsumers + 32)
+yolo_decode_nchw_tma_kernel(const __grid_constant__ CUtensorMap tm, int G, int A, int L, float stride, int train, DecodeAnchors anchors,
+                            int stages, unsigned tiles_per_image, unsigned total_tiles, float* __restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * kTmaTileBytes);
+    uint64_t* empty = full + stages;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int GG = G * G, Ch = A * L;
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tm);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kTmaConsumers / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == kTmaConsumers / 32) {
+        if (lane == 0) {                                     // producer
+            int stage = 0;
+            uint32_t phase = 0;
+            for (unsigned t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const unsigned b = t / tiles_per_image;
+                const int cell0 = (int)(t - b * tiles_per_image) * kTmaTileCells;
+                if (!decode_wait(&empty[stage], phase ^ 1u)) break;
+                mbar_expect_tx(&full[stage], kTmaTileBytes);
+                tma_load_3d(smem + (size_t)stage * kTmaTileBytes, &tm, &full[stage], cell0, 0, (int)b);
+                if (++stage == stages) {
+                    stage = 0;
+                    phase ^= 1u;
                 }
-                __stcs(dst + chl, r);
             }
+        }
+        return;
+    }
+    unsigned plain = 0;                                      // bit i: channel lane + 32 i is a plain sigmoid
+    {
+        int attr = (int)((unsigned)lane % (unsigned)L);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (lane + 32 * i < Ch && attr >= 4) plain |= 1u << i;
+            attr += 32;
+            while (attr >= L) attr -= L;
+        }
+    }
+    const int per_cell = 4 * A;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (unsigned t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const unsigned b = t / tiles_per_image;
+        const int cell0 = (int)(t - b * tiles_per_image) * kTmaTileCells;
+        const int n_cell = min(kTmaTileCells, GG - cell0);
+        const uint8_t* tile = smem + (size_t)stage * kTmaTileBytes;
+        if (!decode_wait(&full[stage], phase)) break;
+        // main pass: one warp per cell, plain sigmoids in one uniform instruction stream
+        for (int cl = warp; cl < n_cell; cl += kTmaConsumers / 32) {
+            float* dst = out + ((size_t)b * GG + cell0 + cl) * Ch + lane;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = swz_tile(tile, lane + 32 * i, cl);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float r = kExact ? sigmoid_f32(v[i]) : sigmoid_fast_f32(v[i]);
+                if ((plain >> i) & 1u) __stcs(dst + 32 * i, r);
+            }
+        }
+        // fix-up: box attributes in the reference's op order, one thread per (cell, anchor, attribute) of the tile
+        for (int it = threadIdx.x; it < n_cell * per_cell; it += kTmaConsumers) {
+            const int cl = it / per_cell, rem = it - cl * per_cell, a = rem >> 2, attr = rem & 3, ch = a * L + attr;
+            const int cell = cell0 + cl, cy = cell / G, cx = cell - cy * G;
+            const float x = swz_tile(tile, ch, cl);
+            float r;
+            if (attr < 2) {
+                r = sigmoid_f32(x);
+                if (!train) r = __fmul_rn(__fadd_rn(r, (float)(attr == 0 ? cx : cy)), stride);
+            } else {
+                float anchor = 0.0f;
+#pragma unroll
+                for (int q = 0; q < RTOD_MAX_ANCHORS; ++q)
+                    if (q == a) anchor = attr == 2 ? anchors.w[q] : anchors.h[q];
+                r = train ? x : __fmul_rn(__fmul_rn(expf(x), anchor), stride);
+            }
+            __stcs(out + ((size_t)b * GG + cell) * Ch + ch, r);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);           // this warp has read the tile
+        if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
         }
     }
 }
@@ -291,11 +438,47 @@ extern "C" int rtod_yolo_decode(const float* head_nchw, int B, int G, int A, int
         anc.h[a] = a < A ? (float)((double)anchors_host[2 * a + 1] / (double)stride) : 0.0f;
     }
     const int L = 5 + C, Ch = A * L, GG = G * G;
-    dim3 grid(ceil_div(GG, kTileCells), B, ceil_div(Ch, kTileCh));
     if (A > 8 || L < 4) return fail(RTOD_ERR_UNSUPPORTED, "rtod_yolo_decode: at most 8 anchors per head");
     static const int exact = getenv("RTOD_DECODE_EXACT") != nullptr;      // full-precision expf for every element
-    yolo_decode_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(head_nchw, G, A, L, (float)stride,
-                                                                    train, exact, anc, out);
+    const int vec = GG % 4 == 0 && (reinterpret_cast<uintptr_t>(head_nchw) & 15u) == 0;      // 16-byte aligned channel rows
+    const bool no_tma = getenv("RTOD_DECODE_NO_TMA") != nullptr;       // tests: the fallback kernel on every shape
+    if (vec && Ch <= kTmaTileCh && !no_tma && (long long)B * GG < (1ll << 31)) {   // TMA-pipelined tiles (see the kernel)
+        static EncodeTiledFn encode_tiled = nullptr;
+        if (!encode_tiled) {
+            const int rc = driver_fn("cuTensorMapEncodeTiled", reinterpret_cast<void**>(&encode_tiled));
+            if (rc) return rc;
+        }
+        CUtensorMap tm;
+        const cuuint64_t dims[3] = {(cuuint64_t)GG, (cuuint64_t)Ch, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)GG * 4, (cuuint64_t)GG * 4 * Ch};
+        const cuuint32_t box[3] = {(cuuint32_t)kTmaTileCells, (cuuint32_t)kTmaTileCh, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = encode_tiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(head_nchw), dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(RTOD_ERR_CUDA, "cuTensorMapEncodeTiled (decode head) failed: %d", (int)r);
+        const int stages_env = getenv("RTOD_DECODE_STAGES") ? atoi(getenv("RTOD_DECODE_STAGES")) : 0;
+        const int stages = stages_env >= 2 && stages_env <= 6 ? stages_env : 2;
+        const int smem = stages * (int)kTmaTileBytes + 1024 + 256;
+        const int per_sm = (227 * 1024) / (smem + 1024);
+        const unsigned per_image = (unsigned)ceil_div(GG, kTmaTileCells), total = (unsigned)B * per_image;
+        unsigned blocks = (unsigned)(kNumSMs * (per_sm < 1 ? 1 : per_sm));
+        if (blocks > total) blocks = total;
+        if (exact) {
+            RTOD_CUDA_OK(cudaFuncSetAttribute(yolo_decode_nchw_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            yolo_decode_nchw_tma_kernel<true><<<blocks, kTmaConsumers + 32, smem, (cudaStream_t)stream_>>>(tm, G, A, L, (float)stride, train, anc, stages, per_image, total, out);
+        } else {
+            RTOD_CUDA_OK(cudaFuncSetAttribute(yolo_decode_nchw_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            yolo_decode_nchw_tma_kernel<false><<<blocks, kTmaConsumers + 32, smem, (cudaStream_t)stream_>>>(tm, G, A, L, (float)stride, train, anc, stages, per_image, total, out);
+        }
+        RTOD_LAUNCH_OK("yolo_decode_nchw_tma_kernel");
+        return RTOD_OK;
+    }
+    {   // fallback (odd G*G, > 256 channels): one 256-channel x 32-cell tile per CTA through padded shared memory
+        const int smem = 256 * 33 * 4;
+        yolo_decode_nchw_kernel<256, 32><<<dim3(ceil_div(GG, 32), B, ceil_div(Ch, 256)), 256, smem, (cudaStream_t)stream_>>>(
+            head_nchw, G, A, L, (float)stride, train, exact, vec, anc, out);
+    }
     RTOD_LAUNCH_OK("yolo_decode_nchw_kernel");
     return RTOD_OK;
 }

@@ -68,6 +68,28 @@ def test_decode_against_oracle_full_heads(grid, inp_dim):
     assert not host.is_cuda and torch.equal(host, got.cpu())
 
 
+@pytest.mark.parametrize("B,grid,inp_dim,classes,train", [(70, 26, 416, 80, False), (3, 52, 416, 80, True), (5, 10, 320, 80, False),
+                                                          (9, 20, 640, 20, False), (2, 76, 608, 80, False)])
+def test_decode_tma_ring_and_one_tile_kernels_agree(monkeypatch, B, grid, inp_dim, classes, train):
+    """G*G % 4 == 0: the TMA-pipelined persistent kernel (more tiles than resident CTAs x stages, ragged last tile of an
+    image, 2 and 3 ring stages) against the oracle and, bit for bit, against the one-tile-per-CTA kernel"""
+    torch.manual_seed(B + grid)
+    x = torch.randn(B, 3 * (5 + classes), grid, grid) * 1.5
+    anchors = [(10, 13), (16, 30), (33, 23)]
+    want = oracle.predict_transform(x.clone(), inp_dim, anchors, classes, False, TRAIN=train)
+    xd = x.cuda()
+    outs = []
+    for stages in ("2", "3"):
+        monkeypatch.setenv("RTOD_DECODE_STAGES", stages)
+        outs.append(predict_transform(xd, inp_dim, anchors, classes, True, TRAIN=train))
+    monkeypatch.delenv("RTOD_DECODE_STAGES")
+    monkeypatch.setenv("RTOD_DECODE_NO_TMA", "1")
+    one_tile = predict_transform(xd, inp_dim, anchors, classes, True, TRAIN=train)
+    monkeypatch.delenv("RTOD_DECODE_NO_TMA")
+    np.testing.assert_allclose(outs[0].cpu().numpy(), want.numpy(), rtol=DEC_RTOL, atol=DEC_ATOL)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], one_tile)
+
+
 def test_decode_rejects_bad_shapes():
     with pytest.raises(RuntimeError):
         predict_transform(torch.zeros(1, 254, 13, 13).cuda(), 416, [(1, 1)] * 3, 80, True)
