@@ -42,6 +42,7 @@ struct StemTcParams {
     const float* bias;                // [C]
     int B, H, W, C, leaky;
     int strips_per_row, total_strips;
+    int no_relay;                     // bring-up switch RTOD_STEM_NO_RELAY: every builder warp polls its barriers itself
     float in_scale;                   // 1 (fp32 frames) or 256/255 (uint8 frames, fed as value / 256): folded into the weights
 };
 
@@ -195,13 +196,20 @@ __global__ void __launch_bounds__(288, 3) stem_tc_kernel(const __grid_constant__
             }
         }
     } else if (warp < 4) {
+        const bool no_relay = p.no_relay != 0;
         // ================= builders: one operand row (= one input column) per thread; threads 0, 1 also rows 128, 129 ====
         for (int local = 0; local < n_mine; ++local) {
             const int s = local % kStages, buf = local & 1;
             const uint32_t use = (uint32_t)(local >> 1);           // how often this buffer has been used before
             // the staged strip has landed; the MMAs that read this operand buffer two strips ago have completed
-            mbar_wait_parked(&in_full[s], (uint32_t)(local / kStages) & 1u);
-            if (local >= 2) mbar_wait_parked(&a_free[buf], (use - 1u) & 1u);
+            // ONE builder warp polls the two barriers, the other three sleep in a named barrier: a polling warp re-issues
+            // its try_wait loop every time the hardware wakes it (ncu: those loops were 18 % of the instructions this
+            // issue-bound kernel executes)
+            if (warp == 0 || no_relay) {
+                mbar_wait_parked(&in_full[s], (uint32_t)(local / kStages) & 1u);
+                if (local >= 2) mbar_wait_parked(&a_free[buf], (use - 1u) & 1u);
+            }
+            if (!no_relay) asm volatile("bar.sync 1, 128;" ::: "memory");
             const uint8_t* st = stage0 + s * kStagePitch;
             uint8_t* a_hi = a_tiles + (size_t)buf * 2 * kATile;
             uint8_t* a_lo = a_hi + kATile;
@@ -321,6 +329,7 @@ int launch_stem_tc(const float* x_f32, const unsigned char* x_u8, int B, int H, 
     // uint8 frames enter as value / 256 (exact in fp16); the weights carry the remaining 256 / 255 of prep_image's
     // value / 255 (scaling them by 1 / 255 instead would push their lo terms into the fp16 subnormals)
     p.in_scale = u8 ? 256.0f / 255.0f : 1.0f;
+    p.no_relay = getenv("RTOD_STEM_NO_RELAY") != nullptr;
     const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)3 * B};
     const cuuint64_t strides[2] = {(cuuint64_t)W * (u8 ? 1 : 4), (cuuint64_t)W * H * (u8 ? 1 : 4)};
     const cuuint32_t box[3] = {(cuuint32_t)(u8 ? kStrip + 32 : kBoxW), 3, 3};
