@@ -473,7 +473,7 @@ def run_b200(args):
                 "launches_per_step": n_tc, "flops_per_step": tc_flops / reps,
                 "avg_launch_ms": seg_conv / max(n_tc, 1), "share_of_forward": seg_conv / fwd_ms}
     dec_bytes = B * plan.n_rows * plan.n_attrs * 8            # fp32 logits in, fp32 prediction out
-    roofline_decode = {"bound": "hbm", "kernel": "yolo_decode_heads_fast_kernel (one launch, all heads)", "ms": decode_ms,
+    roofline_decode = {"bound": "hbm", "kernel": "yolo_decode_heads_ring_kernel (one launch, all heads)", "ms": decode_ms,
                        "achieved": dec_bytes / max(decode_ms, 1e-9) / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                        "frac": dec_bytes / max(decode_ms, 1e-9) / 1e6 / peaks["hbm_gbs"],
                        "traffic": (dec_traffic["dram_bytes_per_launch"] if dec_traffic else None),

@@ -265,6 +265,22 @@ def test_forward_tensor_core_and_cuda_core_paths_agree():
     assert frac_within(a.cpu(), b.cpu(), 2e-3, 2e-3) >= 0.999
 
 
+@pytest.mark.parametrize("cfg_name,reso,batch", [("yolov3", 416, 2), ("yolov3", 608, 1), ("yolov3-tiny", 416, 5)])
+def test_forward_decode_ring_and_streaming_kernels_agree(monkeypatch, cfg_name, reso, batch):
+    """heads decode inside the forward: the bulk-copy ring kernel (default for the 3 x 85 layout) and the streaming kernel
+    produce the same prediction tensor bit for bit; ragged last tiles (13^2 = 169, 19^2 = 361 cells), 2 to 4 ring stages"""
+    cfg, blocks, stream, state = make_network(cfg_name, 4, "calibrated")
+    x = torch.from_numpy(np.random.RandomState(reso).rand(batch, 3, reso, reso).astype(np.float32)).cuda()
+    monkeypatch.setenv("RTOD_DECODE_NO_RING", "1")
+    want = build_model(cfg, state, reso, _lib.PLAN_NO_AUTOTUNE, graph=False)(x)
+    monkeypatch.delenv("RTOD_DECODE_NO_RING")
+    for stages in ("2", "3", "4"):
+        monkeypatch.setenv("RTOD_DECODE_STAGES", stages)
+        got = build_model(cfg, state, reso, _lib.PLAN_NO_AUTOTUNE, graph=False)(x)
+        assert torch.equal(got, want), stages
+    monkeypatch.delenv("RTOD_DECODE_STAGES")
+
+
 # ------------------------------------------------------------------ runtime behaviour
 def test_forward_graph_replay_host_input_and_state_changes():
     cfg, blocks, stream, state = make_network("yolov3-tiny", 8, "calibrated")
