@@ -281,6 +281,19 @@ def test_forward_decode_ring_and_streaming_kernels_agree(monkeypatch, cfg_name, 
     monkeypatch.delenv("RTOD_DECODE_STAGES")
 
 
+@pytest.mark.parametrize("cfg_name,reso,batch", [("yolov3", 416, 2), ("yolov3-tiny", 160, 3), ("yolov3", 608, 1)])
+def test_forward_upsample_block_and_per_output_kernels_agree(monkeypatch, cfg_name, reso, batch):
+    """bilinear x2 (src/darknet.py:591-592): the kernel that builds a 2 x 2 output block per input pixel and the one-thread-
+    per-output kernel evaluate the same expression: identical prediction tensors (5x5 .. 38x38 inputs, clamped borders)"""
+    cfg, blocks, stream, state = make_network(cfg_name, 6, "calibrated")
+    x = torch.from_numpy(np.random.RandomState(reso + batch).rand(batch, 3, reso, reso).astype(np.float32)).cuda()
+    got = build_model(cfg, state, reso, _lib.PLAN_NO_AUTOTUNE, graph=False)(x)
+    monkeypatch.setenv("RTOD_UPSAMPLE_PER_OUTPUT", "1")
+    want = build_model(cfg, state, reso, _lib.PLAN_NO_AUTOTUNE, graph=False)(x)
+    monkeypatch.delenv("RTOD_UPSAMPLE_PER_OUTPUT")
+    assert torch.equal(got, want)
+
+
 # ------------------------------------------------------------------ runtime behaviour
 def test_forward_graph_replay_host_input_and_state_changes():
     cfg, blocks, stream, state = make_network("yolov3-tiny", 8, "calibrated")
