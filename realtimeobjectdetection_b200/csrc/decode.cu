@@ -162,7 +162,7 @@ yolo_decode_nchw_tma_kernel(const __grid_constant__ CUtensorMap tm, int G, int A
             for (unsigned t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const unsigned b = t / tiles_per_image;
                 const int cell0 = (int)(t - b * tiles_per_image) * kTmaTileCells;
-                if (!decode_wait(&empty[stage], phase ^ 1u)) break;
+                if (!decode_wait(&empty[stage], phase ^ 1u)) __trap();       // no plan, no failure flag: fail loudly
                 mbar_expect_tx(&full[stage], kTmaTileBytes);
                 tma_load_3d(smem + (size_t)stage * kTmaTileBytes, &tm, &full[stage], cell0, 0, (int)b);
                 if (++stage == stages) {
@@ -191,7 +191,7 @@ yolo_decode_nchw_tma_kernel(const __grid_constant__ CUtensorMap tm, int G, int A
         const int cell0 = (int)(t - b * tiles_per_image) * kTmaTileCells;
         const int n_cell = min(kTmaTileCells, GG - cell0);
         const uint8_t* tile = smem + (size_t)stage * kTmaTileBytes;
-        if (!decode_wait(&full[stage], phase)) break;
+        if (!decode_wait(&full[stage], phase)) __trap();
         // main pass: one warp per cell, plain sigmoids in one uniform instruction stream
         for (int cl = warp; cl < n_cell; cl += kTmaConsumers / 32) {
             float* dst = out + ((size_t)b * GG + cell0 + cl) * Ch + lane;
@@ -446,7 +446,10 @@ yolo_decode_heads_ring_kernel(DecodeHeads heads, int N, int stages, unsigned til
             for (unsigned t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const RingTile rt = ring_tile(heads, t, tiles_per_image);
                 const int G = heads.grid[rt.h], pitch = heads.pitch[rt.h];
-                if (!decode_wait(&empty[stage], phase ^ 1u)) break;
+                if (!decode_wait(&empty[stage], phase ^ 1u)) {
+                    if (heads.err_flag) raise_device_error(heads.err_flag, 3);
+                    break;
+                }
                 const uint32_t bytes = (uint32_t)rt.n_cell * (uint32_t)pitch * 4u;
                 mbar_expect_tx(&full[stage], bytes);
                 bulk_load_1d(smem + (size_t)stage * stage_bytes, heads.raw[rt.h] + ((size_t)rt.b * G * G + rt.cell0) * pitch, bytes,
@@ -467,7 +470,10 @@ yolo_decode_heads_ring_kernel(DecodeHeads heads, int N, int stages, unsigned til
         const float stride = heads.stride[rt.h];
         const float* tile = reinterpret_cast<const float*>(smem + (size_t)stage * stage_bytes);
         float* out0 = pred + ((size_t)rt.b * N + heads.row_base[rt.h] + (size_t)rt.cell0 * A) * L;
-        if (!decode_wait(&full[stage], phase)) break;
+        if (!decode_wait(&full[stage], phase)) {             // (never in practice: reported like the convolutions' time-outs)
+            if (heads.err_flag && lane == 0) raise_device_error(heads.err_flag, 3);
+            break;
+        }
         // main pass: groups 0-6 are complete, lane 31 of group 7 (element 255) does not exist; box attributes sit in
         // groups 0 (0-3), 2 (85-88) and 5 (170-173) and are left to the fix-up pass
         for (int cl = warp; cl < rt.n_cell; cl += kRingConsumers / 32) {

@@ -21,6 +21,7 @@ struct DecodeHeads {                   // all yolo heads of one plan, in cfg ord
     float stride[kMaxHeads];           // inp_dim / G
     float anchor_w[kMaxHeads][RTOD_MAX_ANCHORS];
     float anchor_h[kMaxHeads][RTOD_MAX_ANCHORS];
+    int* err_flag;                     // the plan's device failure block (tc_ptx.cuh: raise_device_error), may be null
 };
 
 int launch_decode_heads(const DecodeHeads& heads, int B, int N, int L, int train, float* pred,

@@ -625,6 +625,7 @@ static int run_forward(RtodPlan* p, const float* x, float* pred, int train, cuda
     if (ev) RTOD_CUDA_OK(cudaEventRecord(ev[n], stream));
     if (p->heads.count && (rc = mark_segment(seg, 0, stream))) return rc;
     if (p->heads.count) {
+        p->heads.err_flag = p->err_flag;
         rc = launch_decode_heads(p->heads, p->batch, p->n_rows, p->n_attrs, train, pred, stream);
         if (rc) return rc;
     }
