@@ -84,49 +84,89 @@ def synthetic_weights_file(cfg_name, seed=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock, power and throttle reasons of one GPU DURING the timed region (B200_PROFILING.md).
+
+    In-process NVML (pynvml) polled every 20 ms by a thread: `nvidia-smi -lms` -- the fallback when pynvml is missing --
+    takes several hundred ms to start on an 8-GPU box and holds driver locks while it does, which showed up as two
+    75-120 ms stalls of BOTH ranks inside a 0.1 s timed region in about one 2-GPU run out of five."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.handle, self.stop_flag, self.thread = None, None, False, None
+        try:                                                  # NVML is initialised here, well before the timed region
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.handle = pynvml, handle
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.rows.append((time.time(), mhz, self.max_mhz, [n for n, bit in names if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            time.sleep(1.0)                                   # let nvidia-smi finish its start-up outside the timed region
         except OSError:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ts, line in self.rows:
             f = [v.strip() for v in line.split(",")]
-            if len(f) < 8 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                reasons = [name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8])
+                           if v.lower().startswith("active")]
+                self.rows.append((time.time(), float(f[1]), float(f[2]), reasons))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+    def stop(self, t0, t1):
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05 if self.nvml is not None else 0.15)
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, mhz, max_mhz, why in list(self.rows):
+            if not (t0 - 0.02 <= ts <= t1 + 0.02):
+                continue
+            sm.append(mhz)
+            mx.append(max_mhz)
+            reasons.update(why)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sample in timed region"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "how": "NVML polled in-process every 20 ms" if self.nvml is not None else "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------ reference / CPU arm
@@ -314,11 +354,16 @@ def run_b200(args):
         n_seen = 0
         t0 = time.time()
         e0.record()
+        trace = [] if os.environ.get("RTOD_BENCH_STEP_TIMES") else None
         for i in range(n_steps + 1):
             det = step(i) if i < n_steps else collect()      # n_steps enqueued, n_steps results collected
             if det is not None and not isinstance(det, int):
                 n_seen += det.size(0)
+            if trace is not None:
+                trace.append(time.time())
         e1.record()
+        if trace:
+            sys.stderr.write("rank %d host ms per step: %s\n" % (rank, " ".join("%.1f" % ((b - a) * 1e3) for a, b in zip([t0] + trace[:-1], trace))))
         barrier()
         return e0.elapsed_time(e1), n_seen, t0, time.time()
 

@@ -68,10 +68,13 @@ class PendingGather:
         the event recorded behind this gather's own copy -- later work on the compute stream keeps running."""
         if self._work is not None:                           # CPU (gloo) path
             self._work.wait()
+        if self._done is not None:
+            # every rank waits for ITS part of the collective (one step late in a streaming loop): a rank that never
+            # collects anything would run its host arbitrarily far ahead of its GPU, the caching allocator could not
+            # recycle the per-step buffers and its cudaMalloc / cudaFree calls stalled the whole job for 40-120 ms
+            self._done.synchronize()
         if self._rank != self._dst:
             return None
-        if self._done is not None:
-            self._done.synchronize()
         parts = []
         for r in range(self._world):
             n = int(self._bucket_host[r, 0, 0])
@@ -80,10 +83,18 @@ class PendingGather:
                                    "raise `capacity`" % (r, n, self._cap))
             if n:
                 parts.append(self._bucket_host[r, 1:1 + n])
-        return torch.cat(parts, 0).clone() if parts else 0
+        out = torch.cat(parts, 0).clone() if parts else 0
+        if self._done is not None and self._bucket_host is not None:     # the pinned bucket goes back to the pool
+            _PINNED_BUCKETS.setdefault(tuple(self._bucket_host.shape), []).append(self._bucket_host)
+            self._bucket_host = None
+        return out
 
 
 _GATHER_STREAMS = {}
+# pinned host buckets by shape, reused from step to step: a fresh page-locked allocation per step costs a cudaHostAlloc
+# whenever the caching host allocator has no retired block yet -- 15-120 ms stalls of every rank (they wait in the
+# collective) in the first steps of a streaming loop on an 8-GPU box
+_PINNED_BUCKETS = {}
 
 
 def gather_detections_async(rows, count, first_frame: int, capacity: int, group=None, dst: int = 0) -> PendingGather:
@@ -124,10 +135,11 @@ def gather_detections_async(rows, count, first_frame: int, capacity: int, group=
         payload.record_stream(side)
         if rank == dst:
             bucket.record_stream(side)
-            host = torch.empty(bucket.shape, dtype=torch.float32, pin_memory=True)
+            pool = _PINNED_BUCKETS.get(tuple(bucket.shape))
+            host = pool.pop() if pool else torch.empty(bucket.shape, dtype=torch.float32, pin_memory=True)
             host.copy_(bucket, non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(side)
+        done = torch.cuda.Event()
+        done.record(side)
     return PendingGather(rank, dst, world, capacity, host, done, None)
 
 
