@@ -225,6 +225,14 @@ int rtod_rescale_boxes(const float* rows, int D, const float* im_dims, int n_img
 int rtod_bbox_iou_matrix(const float* pred_boxes, int P, int pred_stride, const float* target_boxes, int T,
                          int target_stride, int use_threshold, double threshold, float* out, void* stream);
 
+/* ---- multi-GPU: payload of the per-step detection gather (no reference counterpart: the reference is
+ * single-process) ---------------------------------------------------------
+ * payload: [capacity + 1, 8] fp32.  Row 0 = (count, 0, ...); row 1 + i = rows[i] with column 0 (the image
+ * index) shifted by first_frame for i < min(*count, n_rows), zeros beyond.  `count` is a device int (the
+ * count rtod_write_results stored): nothing is read on the host. */
+int rtod_pack_detections(const float* rows, int n_rows, const int* count, float first_frame, int capacity,
+                         float* payload, void* stream);
+
 /* ---- measurement aid (bench.py "clocks"; no reference counterpart) ------------------------
  * One thread samples the SM clock it runs on: `samples` windows of `interval_us` microseconds,
  * out_mhz[i] = SM cycles / wall time of window i.  Launch it on a side stream next to the work

@@ -84,6 +84,7 @@ _PROTOTYPES = {
                                      ctypes.POINTER(_i)]),
     "rtod_prep_image": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "rtod_rescale_boxes": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "rtod_pack_detections": (_i, [_vp, _i, _vp, _f, _i, _vp, _vp]),
     "rtod_bbox_iou_matrix": (_i, [_vp, _i, _i, _vp, _i, _i, _i, ctypes.c_double, _vp, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(sorted(_PROTOTYPES))

@@ -150,6 +150,27 @@ __global__ void rescale_boxes_kernel(const float* __restrict__ rows, int D, cons
     }
 }
 
+// ---- fixed-capacity gather payload of one rank (sharding.gather_detections_async) ------------------------------------
+// payload row 0 = (count, 0, ...); row 1 + i = detection i with the image column shifted by first_frame for i < count,
+// zeros beyond: one launch instead of the eight small tensor operations it replaces on every step of every rank
+__global__ void pack_detections_kernel(const float* __restrict__ rows, int n_rows, const int* __restrict__ count, float first_frame,
+                                       int capacity, float* __restrict__ payload) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;                     // payload row
+    if (i > capacity) return;
+    const int cnt = *count;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (i == 0) a.x = (float)cnt;
+    else if (i - 1 < cnt && i - 1 < n_rows) {
+        const float4* r = reinterpret_cast<const float4*>(rows + (long long)(i - 1) * 8);
+        a = r[0];
+        b = r[1];
+        a.x = __fadd_rn(a.x, first_frame);
+    }
+    float4* o = reinterpret_cast<float4*>(payload + (long long)i * 8);
+    o[0] = a;
+    o[1] = b;
+}
+
 // ---- test.py:139-151 ---------------------------------------------------------------------------------------------
 // one thread per target and eight predictions; the eight prediction boxes of a CTA sit in shared memory
 __global__ void __launch_bounds__(256) iou_matrix_kernel(const float* __restrict__ pred, int P, int ps, const float* __restrict__ target,
@@ -272,6 +293,18 @@ extern "C" int rtod_rescale_boxes(const float* rows, int D, const float* im_dims
     rescale_boxes_kernel<<<ceil_div(D, 128), 128, 0, (cudaStream_t)stream>>>(rows, D, im_dims, n_img, (float)inp_dim,
                                                                              (float)ref_dim, out_rows, out_dims);
     RTOD_LAUNCH_OK("rescale_boxes_kernel");
+    return RTOD_OK;
+}
+
+extern "C" int rtod_pack_detections(const float* rows, int n_rows, const int* count, float first_frame, int capacity,
+                                    float* payload, void* stream) {
+    if (n_rows < 0 || capacity < 0) return fail(RTOD_ERR_BAD_ARG, "rtod_pack_detections: bad size");
+    if (!count || !payload || (n_rows > 0 && !rows)) return fail(RTOD_ERR_BAD_ARG, "rtod_pack_detections: null pointer");
+    if ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(payload)) & 15u)
+        return fail(RTOD_ERR_BAD_ARG, "rtod_pack_detections: rows / payload must be 16-byte aligned");
+    pack_detections_kernel<<<ceil_div(capacity + 1, 256), 256, 0, (cudaStream_t)stream>>>(rows, n_rows, count, first_frame, capacity,
+                                                                                         payload);
+    RTOD_LAUNCH_OK("pack_detections_kernel");
     return RTOD_OK;
 }
 

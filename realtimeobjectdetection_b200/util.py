@@ -182,7 +182,9 @@ def write_results_async(prediction, num_class, confidence=0.6, nms_conf=0.4) -> 
     B, N, C = x.size(0), x.size(1), int(num_class)
     cap = max(B * N, 1)
     rows = torch.empty(cap, 8, dtype=torch.float32, device=dev)
-    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    # (rtod_write_results always stores the count -- the last image's CTA writes it unconditionally -- so only the
+    # empty-tensor path, which makes no call, needs a zero: one fill launch less on the batch-1 latency path)
+    count = torch.empty(1, dtype=torch.int32, device=dev) if B > 0 and N > 0 else torch.zeros(1, dtype=torch.int32, device=dev)
     count_host = _PINNED_COUNTS.pop() if _PINNED_COUNTS else torch.zeros(1, dtype=torch.int32).pin_memory()
     event = torch.cuda.Event()
     if B > 0 and N > 0:

@@ -458,6 +458,14 @@ def test_sharded_detection_over_nccl_single_rank():
         h = write_results_async(model(x.cuda()), 80, 0.3, 0.4)
         got = gather_detections_async(h.rows_device, h.count_device, 0, capacity=want.size(0) + 5).result()
         assert torch.equal(got, want.cpu())
+        h = write_results_async(model(x.cuda()), 80, 0.3, 0.4)              # image column shifted by the rank's first frame
+        got = gather_detections_async(h.rows_device, h.count_device, 6, capacity=want.size(0)).result()
+        shifted = want.cpu().clone()
+        shifted[:, 0] += 6.0
+        assert torch.equal(got, shifted)
+        h = write_results_async(model(x.cuda()), 80, 0.3, 0.4)              # more detections than the fixed capacity: loud
+        with pytest.raises(RuntimeError):
+            gather_detections_async(h.rows_device, h.count_device, 0, capacity=want.size(0) - 1).result()
         pipe = DetectionPipeline(model, 80, 0.3, 0.4, gather={"first_frame": 0, "capacity": want.size(0) + 5})
         outs = list(pipe.run([x.pin_memory(), x.pin_memory()]))
         assert len(outs) == 2 and all(torch.equal(o, want.cpu()) for o in outs)

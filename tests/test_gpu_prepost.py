@@ -85,3 +85,23 @@ def test_iou_matrix_large_against_oracle():
     got = bbox_iou_matrix(pred.cuda(), target.cuda(), 0.3).cpu()
     assert torch.equal(got, torch.where(want.double() > 0.3, want, torch.zeros_like(want)))
     assert bbox_iou_matrix(pred[:0], target).shape == (0, 400)
+
+
+@pytest.mark.parametrize("n_rows,count,capacity,first", [(50, 17, 40, 128), (50, 0, 8, 0), (10, 10, 10, 64), (30, 45, 20, 3), (0, 0, 5, 7)])
+def test_pack_detections_payload(n_rows, count, capacity, first):
+    """rtod_pack_detections (the per-step gather payload of a rank): row 0 carries the count, rows 1.. the first
+    min(count, n_rows, capacity) detections with the image column shifted, zeros beyond -- what the tensor expression
+    of sharding.gather_detections_async builds (which multiplies stale rows by 0 instead of overwriting them)"""
+    from realtimeobjectdetection_b200 import _lib
+    rng = np.random.RandomState(n_rows + count)
+    rows = torch.from_numpy(rng.rand(max(n_rows, 1), 8).astype(np.float32)).cuda()
+    cnt = torch.tensor([count], dtype=torch.int32, device="cuda")
+    payload = torch.full((capacity + 1, 8), float("nan"), device="cuda")
+    n_src = min(capacity, n_rows)
+    _lib.check(_lib.load().rtod_pack_detections(rows.data_ptr(), n_src, cnt.data_ptr(), float(first), capacity, payload.data_ptr(), None))
+    want = torch.zeros(capacity + 1, 8)
+    want[0, 0] = float(count)
+    n = min(count, n_src)
+    want[1:1 + n] = rows[:n].cpu()
+    want[1:1 + n, 0] += float(first)
+    assert torch.equal(payload.cpu(), want)
