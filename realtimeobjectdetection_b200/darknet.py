@@ -62,6 +62,10 @@ class DetectionLayer(nn.Module):
         return predict_transform(x.data, inp_dim, self.anchors, num_classes, CUDA=self.CUDA)
 
 
+_CUDA_SEEN = False
+_EAGER_WEIGHT_CHECK = os.environ.get("RTOD_EAGER_WEIGHT_CHECK") == "1"     # A/B switch: version counters read before the launch
+
+
 class _Plan:
     """A bound librtod execution plan for one input shape on one device."""
 
@@ -93,10 +97,12 @@ class _Plan:
                              in_w >= 160 and in_w % 16 == 0)
         # failure reporting without a sync: kernels store a code in this pinned, device-mapped int on time-out
         self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.err_np = self.err_host.numpy()                # (indexing a tensor costs microseconds on the batch-1 path)
         with torch.cuda.device(device):
             _lib.check(lib.rtod_plan_set_error_sink(self.handle, self.err_host.data_ptr(),
                                                     torch.cuda.current_stream(device).cuda_stream))
-        self.weight_version = None
+        self.weight_version = None                         # _weights_signature() of the last weight sync
+        self.weight_epoch = None                           # ... and its cheap part (Darknet._weights_epoch)
         # CUDA graphs of the launch sequence, keyed by (input pointer, train): {"graph", "x", "pred"}.
         # Key (dtype, train) = the staging graph of that input type (input copied into its own buffer first).
         self.graphs = {}
@@ -108,10 +114,10 @@ class _Plan:
 
     def raise_if_failed(self):
         """Raise (and re-arm the plan) if a kernel of an earlier forward reported a device-side failure."""
-        code = int(self.err_host[0])
+        code = int(self.err_np[0])
         if code == 0:
             return
-        self.err_host[0] = 0
+        self.err_np[0] = 0
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device)
             stream.synchronize()
@@ -157,6 +163,7 @@ class Darknet(nn.Module):
         self.borrow_output = False
         self._warned_train_bn = False
         self._warned_grad = False
+        self._yolo_side = None                             # (anchors, classes) the yolo branch publishes, cached
 
     # ------------------------------------------------------------------ reference accessors
     def get_blocks(self) -> list:
@@ -366,8 +373,9 @@ class Darknet(nn.Module):
         plan.last_used = self._plan_clock
         return plan
 
-    def _sync_weights(self, plan: _Plan, stream: int):
-        sig = self._weights_signature()
+    def _sync_weights(self, plan: _Plan, stream: int, sig=None):
+        if sig is None:
+            sig = self._weights_signature()
         if plan.weight_version == sig:
             return
         lib = plan.lib
@@ -395,6 +403,7 @@ class Darknet(nn.Module):
                 float(bn.eps) if bn is not None else 0.0, stream))
         torch.cuda.current_stream(dev).synchronize()       # staging copies in `keep` may now die
         plan.weight_version = sig
+        plan.weight_epoch = self._weights_epoch
         plan.graphs.clear()                                 # weights live in the same arena: the graphs stay
         # valid, but re-capture keeps the contract simple
 
@@ -407,9 +416,12 @@ class Darknet(nn.Module):
         reference trainer, train.py:412-425, is out of scope -- a warning is issued once if a
         gradient is expected).
         """
+        global _CUDA_SEEN
         lib = _lib.load()
-        if not torch.cuda.is_available():
-            raise RuntimeError("Darknet.forward needs a CUDA device (B200, sm_100a); no CPU fallback")
+        if not _CUDA_SEEN:                                   # (asked once: the query costs microseconds per call)
+            if not torch.cuda.is_available():
+                raise RuntimeError("Darknet.forward needs a CUDA device (B200, sm_100a); no CPU fallback")
+            _CUDA_SEEN = True
         if self.training and not self._warned_train_bn:
             self._warned_train_bn = True
             warnings.warn("Darknet is in training mode; this implementation always evaluates "
@@ -444,23 +456,41 @@ class Darknet(nn.Module):
             plan = self._get_plan(key, device)
             plan.raise_if_failed()                           # a time-out reported by an earlier forward
             stream = torch.cuda.current_stream(device)
-            self._sync_weights(plan, stream.cuda_stream)
             has_heads = plan.n_rows > 0
+            # Weights are re-ingested when a parameter / buffer changed since the plan's last sync.  The exact test reads
+            # the version counter of all ~370 tensors (~45 us of Python): on the graph-replay path -- the batch-1
+            # latency path -- the replay is launched FIRST with the weights of the last sync and the counters are read
+            # while the GPU works; in the rare case that something did change, the weights are re-ingested and the
+            # forward runs again (same result as checking first, the check is off the critical path).  load_weights /
+            # load_state_dict / .to() bump a cheap epoch, which is always checked before the launch.
+            deferred = (has_heads and self.use_cuda_graph and plan.calls >= 1 and plan.weight_version is not None and
+                        plan.weight_epoch == self._weights_epoch and not _EAGER_WEIGHT_CHECK and
+                        not torch.cuda.is_current_stream_capturing())
+            if not deferred:
+                self._sync_weights(plan, stream.cuda_stream)
             if x.dtype == torch.uint8 and not plan.takes_u8:
                 x = x.to(torch.float32) / 255.0                  # (bf16 storage / unusual stems: scale here)
             pred = self._run(plan, x, int(bool(self.TRAIN)), stream) if has_heads else None
+            if deferred:
+                sig = self._weights_signature()
+                if sig != plan.weight_version:                   # a tensor was modified in place: redo with the new weights
+                    self._sync_weights(plan, stream.cuda_stream, sig)
+                    pred = self._run(plan, x, int(bool(self.TRAIN)), stream)
             if not has_heads:
                 _lib.check(plan.forward_fn(x)(plan.handle, x.data_ptr(), None, 0, stream.cuda_stream))
 
-        # side effects of the reference's yolo branch (:239-243, :260)
-        anchors, classes = [], None
-        for i, block in enumerate(self.blocks[1:]):
-            if block["type"] == "yolo":
-                anchors.extend(self.module_list[i][0].anchors)
-                classes = int(block["classes"])
-        if classes is not None:
-            self.anchors = anchors
-            self.num_classes = classes
+        # side effects of the reference's yolo branch (:239-243, :260); blocks and modules are fixed after construction
+        side = self._yolo_side
+        if side is None:
+            anchors, classes = [], None
+            for i, block in enumerate(self.blocks[1:]):
+                if block["type"] == "yolo":
+                    anchors.extend(self.module_list[i][0].anchors)
+                    classes = int(block["classes"])
+            side = self._yolo_side = (tuple(anchors), classes)
+        if side[1] is not None:
+            self.anchors = list(side[0])
+            self.num_classes = side[1]
         plan.calls += 1
         return pred if has_heads else []
 

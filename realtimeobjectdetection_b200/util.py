@@ -133,9 +133,9 @@ class PendingDetections:
         ``to_host``: copy the rows to the host on a side stream instead of the compute stream."""
         if self._count_host is not None:
             self._event.synchronize()
-            self._d = int(self._count_host[0])
+            self._d = int(self._count_np[0])                  # (numpy view: indexing the tensor costs microseconds)
             if len(_PINNED_COUNTS) < 64:
-                _PINNED_COUNTS.append(self._count_host)        # recycled: no host allocation per call
+                _PINNED_COUNTS.append((self._count_host, self._count_np))    # recycled: no host allocation per call
             self._count_host = None
         d = self._d
         if d < 0:
@@ -159,7 +159,7 @@ class PendingDetections:
 
 
 _SIDE_STREAMS = {}
-_PINNED_COUNTS = []                                     # recycled 1-element pinned int32 tensors
+_PINNED_COUNTS = []                                     # recycled (1-element pinned int32 tensor, its numpy view) pairs
 
 
 def _side_stream(device):
@@ -185,7 +185,11 @@ def write_results_async(prediction, num_class, confidence=0.6, nms_conf=0.4) -> 
     # (rtod_write_results always stores the count -- the last image's CTA writes it unconditionally -- so only the
     # empty-tensor path, which makes no call, needs a zero: one fill launch less on the batch-1 latency path)
     count = torch.empty(1, dtype=torch.int32, device=dev) if B > 0 and N > 0 else torch.zeros(1, dtype=torch.int32, device=dev)
-    count_host = _PINNED_COUNTS.pop() if _PINNED_COUNTS else torch.zeros(1, dtype=torch.int32).pin_memory()
+    if _PINNED_COUNTS:
+        count_host, count_np = _PINNED_COUNTS.pop()
+    else:
+        count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        count_np = count_host.numpy()
     event = torch.cuda.Event()
     if B > 0 and N > 0:
         nbytes = lib.rtod_write_results_workspace_bytes(B, N, C)
@@ -198,6 +202,7 @@ def write_results_async(prediction, num_class, confidence=0.6, nms_conf=0.4) -> 
     count_host.copy_(count, non_blocking=True)
     event.record(torch.cuda.current_stream(dev))
     pending = PendingDetections(rows, count_host, event, home, cap, dev)
+    pending._count_np = count_np
     pending._keep = (x, count)                                 # alive until the kernels have run
     pending.count_device = count
     return pending
