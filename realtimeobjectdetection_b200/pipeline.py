@@ -41,6 +41,7 @@ class DetectionPipeline:
         self._slots = []
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._spec_rows = 256                                  # rows copied to the host speculatively with the count
 
     def _slot(self, k, like):
         while len(self._slots) <= k:
@@ -99,7 +100,10 @@ class DetectionPipeline:
                     pass
                 compute.wait_event(pending["ready"])
                 pred = self.model(self._network_input(pending))
-                handle = write_results_async(pred, self.num_class, self.confidence, self.nms_conf)
+                # (no gather: the rows go to this host -- copy as many as the previous batch needed, rounded up, together
+                # with the count, so that collecting them costs one synchronisation instead of two)
+                handle = write_results_async(pred, self.num_class, self.confidence, self.nms_conf,
+                                             host_rows=0 if self.gather is not None else self._spec_rows)
                 pending["free"].record(compute)
                 if self.gather is not None:
                     from .sharding import gather_detections_async
@@ -125,8 +129,15 @@ class DetectionPipeline:
             if det is not None:
                 self.d2h_bytes += handle.bucket_bytes
             return det
+        spec = getattr(handle, "_host_rows", None)
+        spec_rows = 0 if spec is None else spec.size(0)          # rows copied speculatively (all of them cross the bus)
         det = handle.result(to_host=True)
+        self.d2h_bytes += spec_rows * 32
         if not isinstance(det, int):
-            self.d2h_bytes += det.numel() * 4
+            if det.size(0) > spec_rows:
+                self.d2h_bytes += det.numel() * 4                 # did not fit: the exact-size copy on top
+            want = ((det.size(0) * 5 // 4 + 255) // 256) * 256          # 25 % head room, in steps of 256 rows
+            if want > self._spec_rows or want * 4 < self._spec_rows:
+                self._spec_rows = max(256, want)
         self.d2h_bytes += 4                                    # the detection count
         return det

@@ -125,6 +125,7 @@ class PendingDetections:
         self._home, self._cap, self._device = home, cap, device
         self._d = None
         self.rows_device = rows              # [cap, 8]: the first count_device[0] rows are the detections
+        self._host_rows = None               # pinned [K, 8]: speculative copy of the first K rows (write_results_async)
         self.count_device = None             # int32 [1] on the device (set by write_results_async)
 
     def result(self, to_host: bool = False):
@@ -138,6 +139,16 @@ class PendingDetections:
                 _PINNED_COUNTS.append((self._count_host, self._count_np))    # recycled: no host allocation per call
             self._count_host = None
         d = self._d
+        spec_out = None
+        if self._host_rows is not None:
+            # the first rows were copied to pinned memory in the stream, behind the kernels and before the event: they
+            # are on the host already -- no second copy, no second synchronisation when the count fits
+            buf, self._host_rows = self._host_rows, None
+            if 0 < d <= buf.size(0):
+                spec_out = buf[:d].clone()
+            pool = _PINNED_ROWS.setdefault(buf.size(0), [])
+            if len(pool) < 8:
+                pool.append(buf)
         if d < 0:
             raise RuntimeError("write_results: device-side failure (a bounded wait in the NMS kernels timed out)")
         if d == 0:
@@ -145,6 +156,8 @@ class PendingDetections:
         if d > self._cap:
             raise RuntimeError("write_results: %d detections exceed capacity %d" % (d, self._cap))
         if to_host or self._home.type == "cpu":
+            if spec_out is not None:
+                return spec_out
             side = _side_stream(self._device)
             out = torch.empty(d, 8, dtype=torch.float32, pin_memory=True)
             with torch.cuda.stream(side):
@@ -160,6 +173,7 @@ class PendingDetections:
 
 _SIDE_STREAMS = {}
 _PINNED_COUNTS = []                                     # recycled (1-element pinned int32 tensor, its numpy view) pairs
+_PINNED_ROWS = {}                                       # K -> recycled pinned [K, 8] buffers of the speculative row copy
 
 
 def _side_stream(device):
@@ -169,7 +183,7 @@ def _side_stream(device):
     return _SIDE_STREAMS[key]
 
 
-def write_results_async(prediction, num_class, confidence=0.6, nms_conf=0.4) -> PendingDetections:
+def write_results_async(prediction, num_class, confidence=0.6, nms_conf=0.4, host_rows: int = 0) -> PendingDetections:
     """``write_results`` split in two: this call enqueues scan + per-image NMS + emit and returns at once;
     ``.result()`` yields what ``write_results`` returns.  A streaming loop enqueues the next batch's forward
     before collecting, so the GPU never waits for the host (``DetectionPipeline``)."""
@@ -200,9 +214,18 @@ def write_results_async(prediction, num_class, confidence=0.6, nms_conf=0.4) -> 
                                               rows.data_ptr(), cap, count.data_ptr(), ws_ptr, nbytes,
                                               _stream_ptr(dev)))
     count_host.copy_(count, non_blocking=True)
+    spec = None
+    if host_rows > 0 and B > 0 and N > 0:
+        # the caller will want the rows on the host (``result(to_host=True)``): copy the first `host_rows` of them to
+        # pinned memory now, in the stream -- when the count turns out to fit, the detections arrive with it
+        k = min(int(host_rows), cap)
+        pool = _PINNED_ROWS.get(k)
+        spec = pool.pop() if pool else torch.empty(k, 8, dtype=torch.float32).pin_memory()
+        spec.copy_(rows[:k], non_blocking=True)
     event.record(torch.cuda.current_stream(dev))
     pending = PendingDetections(rows, count_host, event, home, cap, dev)
     pending._count_np = count_np
+    pending._host_rows = spec
     pending._keep = (x, count)                                 # alive until the kernels have run
     pending.count_device = count
     return pending
