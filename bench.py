@@ -340,7 +340,7 @@ def run_b200(args):
 
         def step(i):
             pred = net(batches[i & 1])
-            handle = write_results_async(pred, CLASSES, CONF, NMS)
+            handle = write_results_async(pred, CLASSES, CONF, NMS, device_count=world > 1)
             if world > 1:
                 handle = gather_detections_async(handle.rows_device, handle.count_device, first_frame, capacity)
             det = collect()

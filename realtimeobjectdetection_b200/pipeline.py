@@ -103,7 +103,8 @@ class DetectionPipeline:
                 # (no gather: the rows go to this host -- copy as many as the previous batch needed, rounded up, together
                 # with the count, so that collecting them costs one synchronisation instead of two)
                 handle = write_results_async(pred, self.num_class, self.confidence, self.nms_conf,
-                                             host_rows=0 if self.gather is not None else self._spec_rows)
+                                             host_rows=0 if self.gather is not None else self._spec_rows,
+                                             device_count=self.gather is not None)
                 pending["free"].record(compute)
                 if self.gather is not None:
                     from .sharding import gather_detections_async

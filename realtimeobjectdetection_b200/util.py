@@ -126,7 +126,17 @@ class PendingDetections:
         self._d = None
         self.rows_device = rows              # [cap, 8]: the first count_device[0] rows are the detections
         self._host_rows = None               # pinned [K, 8]: speculative copy of the first K rows (write_results_async)
-        self.count_device = None             # int32 [1] on the device (set by write_results_async)
+        self.count_device = None             # int32 [1] on the device (set by write_results_async; None: count on the host only)
+        self._count_np = None
+
+    def __del__(self):
+        # dropped without result(): the kernels may still be about to write the pinned count word -- park it until
+        # its event has completed instead of letting the host allocator hand it to somebody else
+        try:
+            if self._count_host is not None and len(_ORPHANS) < 1024:
+                _ORPHANS.append((self._event, self._count_host, self._count_np))
+        except Exception:
+            pass
 
     def result(self, to_host: bool = False):
         """``[D, 8]`` rows or the int ``0`` (the reference's convention).  Waits only for the event recorded
@@ -173,6 +183,7 @@ class PendingDetections:
 
 _SIDE_STREAMS = {}
 _PINNED_COUNTS = []                                     # recycled (1-element pinned int32 tensor, its numpy view) pairs
+_ORPHANS = []                                           # (event, pinned count, view) of handles dropped before result()
 _PINNED_ROWS = {}                                       # K -> recycled pinned [K, 8] buffers of the speculative row copy
 
 
@@ -183,7 +194,8 @@ def _side_stream(device):
     return _SIDE_STREAMS[key]
 
 
-def write_results_async(prediction, num_class, confidence=0.6, nms_conf=0.4, host_rows: int = 0) -> PendingDetections:
+def write_results_async(prediction, num_class, confidence=0.6, nms_conf=0.4, host_rows: int = 0,
+                        device_count: bool = True) -> PendingDetections:
     """``write_results`` split in two: this call enqueues scan + per-image NMS + emit and returns at once;
     ``.result()`` yields what ``write_results`` returns.  A streaming loop enqueues the next batch's forward
     before collecting, so the GPU never waits for the host (``DetectionPipeline``)."""
@@ -198,12 +210,24 @@ def write_results_async(prediction, num_class, confidence=0.6, nms_conf=0.4, hos
     rows = torch.empty(cap, 8, dtype=torch.float32, device=dev)
     # (rtod_write_results always stores the count -- the last image's CTA writes it unconditionally -- so only the
     # empty-tensor path, which makes no call, needs a zero: one fill launch less on the batch-1 latency path)
-    count = torch.empty(1, dtype=torch.int32, device=dev) if B > 0 and N > 0 else torch.zeros(1, dtype=torch.int32, device=dev)
+    while _ORPHANS and _ORPHANS[0][0].query():             # parked count words whose kernels have finished
+        _, ch, cn = _ORPHANS.pop(0)
+        if len(_PINNED_COUNTS) < 64:
+            _PINNED_COUNTS.append((ch, cn))
     if _PINNED_COUNTS:
         count_host, count_np = _PINNED_COUNTS.pop()
     else:
         count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         count_np = count_host.numpy()
+    # device_count=False (nobody reads the count on the device: no gather): the kernels store it straight into the
+    # pinned word -- page-locked memory is device-addressable under unified addressing, like the plans' failure word --
+    # instead of a device int that a copy node then brings over: one node less at the end of every step
+    if device_count:
+        count = torch.empty(1, dtype=torch.int32, device=dev) if B > 0 and N > 0 else torch.zeros(1, dtype=torch.int32, device=dev)
+        count_ptr = count.data_ptr()
+    else:
+        count, count_ptr = None, count_host.data_ptr()
+        count_np[0] = 0
     event = torch.cuda.Event()
     if B > 0 and N > 0:
         nbytes = lib.rtod_write_results_workspace_bytes(B, N, C)
@@ -211,9 +235,10 @@ def write_results_async(prediction, num_class, confidence=0.6, nms_conf=0.4, hos
         ws_ptr = (ws.data_ptr() + 255) // 256 * 256
         with torch.cuda.device(dev):
             _lib.check(lib.rtod_write_results(x.data_ptr(), B, N, C, float(confidence), float(nms_conf),
-                                              rows.data_ptr(), cap, count.data_ptr(), ws_ptr, nbytes,
+                                              rows.data_ptr(), cap, count_ptr, ws_ptr, nbytes,
                                               _stream_ptr(dev)))
-    count_host.copy_(count, non_blocking=True)
+    if count is not None:
+        count_host.copy_(count, non_blocking=True)
     spec = None
     if host_rows > 0 and B > 0 and N > 0:
         # the caller will want the rows on the host (``result(to_host=True)``): copy the first `host_rows` of them to
@@ -239,7 +264,7 @@ def write_results(prediction, num_class, confidence=0.6, nms_conf=0.4):
     test ``type(x) == int``).  Rows of one (image, class) with bit-equal objectness are ordered
     by row index (the reference's ``torch.sort`` leaves that order unspecified).
     """
-    return write_results_async(prediction, num_class, confidence, nms_conf).result()
+    return write_results_async(prediction, num_class, confidence, nms_conf, device_count=False).result()
 
 
 # ---------------------------------------------------------------------------------------------------
