@@ -106,6 +106,7 @@ class _Plan:
         # CUDA graphs of the launch sequence, keyed by (input pointer, train): {"graph", "x", "pred"}.
         # Key (dtype, train) = the staging graph of that input type (input copied into its own buffer first).
         self.graphs = {}
+        self.last_ptr = None                               # input pointer of the previous graph-path forward
         self.calls = 0
         self.last_used = 0
 
@@ -505,11 +506,18 @@ class Darknet(nn.Module):
         # The launch sequence is replayed as a CUDA graph.  A graph embeds its input pointer: inputs that keep
         # arriving in the same buffers (the pipeline's ring slots, a benchmark's resident batches) get a graph
         # of their own -- no staging copy; any other input is copied into the staging graph's buffer.
-        entry = plan.graphs.get((x.data_ptr(), train))
-        if entry is not None and entry["x"].dtype != x.dtype:
+        ptr = x.data_ptr()
+        entry = plan.graphs.get((ptr, train))
+        if entry is not None and entry["dtype"] != x.dtype:
             entry = None
-        if entry is None and self.borrow_output and len(plan.graphs) < 6:
-            entry = self._capture(plan, x, train, stream, key=(x.data_ptr(), train))
+        # (reference call semantics, borrow_output False: a caller that keeps passing the SAME buffer -- seen on two
+        # consecutive calls -- gets a graph on that pointer too, without the graph holding on to the caller's tensor:
+        # no staging copy in front of the replay on the batch-1 latency path)
+        if entry is None and len(plan.graphs) < 6 and (self.borrow_output or ptr == plan.last_ptr):
+            entry = self._capture(plan, x, train, stream, key=(ptr, train))
+            if entry is not None and not self.borrow_output:
+                entry["x"] = None
+        plan.last_ptr = ptr
         if entry is None:
             entry = plan.graphs.get((str(x.dtype), train))
             if entry is None:
@@ -523,7 +531,7 @@ class Darknet(nn.Module):
 
     def _capture(self, plan: _Plan, x: torch.Tensor, train: int, stream, key):
         shape = (plan.key[0], plan.n_rows, plan.n_attrs)
-        entry = {"x": x, "pred": torch.empty(shape, dtype=torch.float32, device=plan.device),
+        entry = {"x": x, "dtype": x.dtype, "pred": torch.empty(shape, dtype=torch.float32, device=plan.device),
                  "graph": torch.cuda.CUDAGraph()}
         try:
             stream.synchronize()
